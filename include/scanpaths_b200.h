@@ -1,0 +1,169 @@
+/* scanpaths_b200 -- C ABI of the B200-native scanpath sampling + scoring path.
+ *
+ * This is the drop-in boundary.  The reference (chenxy99/Scanpaths) is pure
+ * Python and has no FFI of its own; each entry point below replaces one of the
+ * Python callables that the reference's train.py / test.py import (file:line
+ * cited per function, paths relative to the reference root, identical in
+ * OSIE/, AiR/, COCO_Search18/ unless noted).  INTEGRATION.md shows the ctypes
+ * stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (e.g. a
+ *     torch tensor's data_ptr()); h_* is a HOST pointer.  Nothing is allocated,
+ *     freed or synchronised inside; work is enqueued on `stream`.
+ *   - every function returns 0 on success or a negative spb_status; the message
+ *     of the last failure on the calling thread is spb_last_error().
+ *   - plain C types only.  There is no CPU fallback: without a CUDA device the
+ *     launch functions return SPB_ERR_CUDA.
+ */
+#ifndef SCANPATHS_B200_H
+#define SCANPATHS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *spb_stream; /* cudaStream_t */
+
+enum spb_status {
+    SPB_OK = 0,
+    SPB_ERR_ARG = -1,       /* bad argument (null pointer, size out of range) */
+    SPB_ERR_CUDA = -2,      /* CUDA runtime / driver error (message has the cudaError string) */
+    SPB_ERR_WORKSPACE = -3, /* caller-provided workspace too small */
+    SPB_ERR_UNSUPPORTED = -4
+};
+
+int spb_version(void);
+const char *spb_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * ScanMatch configuration and tables  (utils/evaltools/scanmatch.py:43-114)
+ * ---------------------------------------------------------------------- */
+typedef struct spb_scanmatch_cfg {
+    int32_t Xres, Yres, Xbin, Ybin;
+    double Threshold, GapValue, TempBin, OffsetX, OffsetY;
+} spb_scanmatch_cfg;
+
+/* Host helper mirroring ScanMatch.CreateSubMatrix / GridMask.
+ *   h_sub_delta [Ybin*Xbin]: substitution score as a function of (|d row|, |d col|)
+ *                            (SubMatrix[a,b] depends only on those; bit-equal to it)
+ *   h_sub_full  [nb*nb] or NULL: the full SubMatrix, nb = Xbin*Ybin
+ *   h_xlut [Xres], h_ylut [Yres]: pixel -> bin column / row (the float-arange LUT)
+ *   h_max_sub: numpy.max(SubMatrix), the score normaliser (scanmatch.py:191)      */
+int spb_scanmatch_tables(const spb_scanmatch_cfg *cfg, double *h_sub_delta, double *h_sub_full,
+                         uint8_t *h_xlut, uint8_t *h_ylut, double *h_max_sub);
+
+/* Everything the scoring kernels need besides the scanpaths. */
+typedef struct spb_score_cfg {
+    spb_scanmatch_cfg sm;          /* sm.TempBin is the with-duration bin (50 ms in evaluation.py:159) */
+    int32_t sed_height, sed_width, sed_n; /* stimulus (240, 320), n = 5 (visual_attention_metrics.py:301-309) */
+    int32_t reserved;
+    double stde_max_dim;           /* max(np.shape(stimulus)) = 320 (:407) */
+    double dur_scale;              /* duration multiplier applied first: 1000 (s -> ms, evaluation.py:182) */
+    double max_sub;                /* from spb_scanmatch_tables */
+    const double *d_sub_delta;     /* device copies of the tables */
+    const uint8_t *d_xlut;
+    const uint8_t *d_ylut;
+} spb_score_cfg;
+
+/* ------------------------------------------------------------------------
+ * K1 scanpath_prep: fixations -> symbols, once per scanpath (not per pair).
+ * Replaces ScanMatch.fixationToSequence x2 (scanmatch.py:116-133),
+ * _scanpath_to_string (visual_attention_metrics.py:288-298) and the STDE
+ * rescaling (:409-415).
+ *   d_xyd [n_paths, lmax, 3] f64 (x, y, duration), d_len [n_paths]
+ * out (the "symbol pack"):
+ *   d_sym [n_paths, lmax] u8      ScanMatch bin symbol of each fixation (w/o-duration string)
+ *   d_run [n_paths, lmax] i32     temporal-bin repeat count (with-duration string = sym repeated run times)
+ *   d_nwd [n_paths] i32           length of the with-duration string (sum of runs)
+ *   d_sed [n_paths, lmax] i32     SED grid symbol (chr(97+sq) in the reference)
+ *   d_xyn [n_paths, lmax, 2] f64  x / max_dim, y / max_dim                                  */
+int spb_prep_paths(const double *d_xyd, const int32_t *d_len, int64_t n_paths, int32_t lmax,
+                   const spb_score_cfg *cfg, uint8_t *d_sym, int32_t *d_run, int32_t *d_nwd,
+                   int32_t *d_sed, double *d_xyn, spb_stream stream);
+
+typedef struct spb_path_pack {
+    const uint8_t *d_sym;
+    const int32_t *d_run;
+    const int32_t *d_nwd;
+    const int32_t *d_sed;
+    const double *d_xyn;
+    const int32_t *d_len;
+    int64_t n_paths;
+    int32_t lmax;
+    int32_t reserved;
+} spb_path_pack;
+
+/* ------------------------------------------------------------------------
+ * K2-K4 score_pairs: one warp per (human, simulated) pair, anti-diagonal
+ * wavefront DPs.  Replaces, per pair, ScanMatch.match with and without
+ * duration (scanmatch.py:135-150, 190-193; score only -- every caller drops
+ * align and F), string_edit_distance (visual_attention_metrics.py:301-317) and
+ * scaled_time_delay_embedding_similarity (:393-441).
+ *   pair p scores human path d_pair_h[p] (first argument of the reference
+ *   calls) against simulated path d_pair_s[p]; both packs may be the same
+ *   (human_evaluation).
+ *   d_scores [n_pairs, 4] f64 = (ScanMatch with duration, ScanMatch w/o duration, SED, STDE);
+ *   NaN where the reference yields NaN / None (both strings empty; a path empty).
+ *   d_workspace: only used when a simulated with-duration string exceeds 256
+ *   symbols; spb_score_workspace_bytes(max human nwd) bytes, may be NULL otherwise.
+ *   d_err: device int32 set non-zero if a pair needed more workspace than given.   */
+int64_t spb_score_workspace_bytes(int64_t max_human_nwd);
+int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const int32_t *d_pair_h,
+                    const int32_t *d_pair_s, int64_t n_pairs, const spb_score_cfg *cfg, double *d_scores,
+                    void *d_workspace, int64_t workspace_bytes, int32_t *d_err, spb_stream stream);
+
+/* ------------------------------------------------------------------------
+ * a7 reductions of the score table.  Replaces the aggregation halves of
+ * pairs_eval (OSIE/utils/evaluation.py:325-338) and pairs_eval_scanmatch
+ * (COCO_Search18/utils/evaluation.py:342-349) for a table laid out
+ * [n_groups, group_size, 4] (one group = one simulated path against the S
+ * subjects of its image).
+ *   d_valid [n_groups, group_size] u8 or NULL: rows dropped by the MultiMatch
+ *   NaN rule (either path shorter than min_len_valid); rows whose
+ *   scores are NaN are dropped too.
+ *   d_out [n_groups, 11] f32: slots 5..10 = SM w/o duration, SM with duration,
+ *   SED mean, STDE mean, SED best (min), STDE best (max); means divide by
+ *   group_size; slots 0..4 (MultiMatch, out of scope) NaN; all NaN if no row survives.
+ *   d_reward [n_groups] f64 or NULL: harmonic mean of slots 5, 6 (train.py:252).  */
+int spb_reduce_pairs_eval(const double *d_scores, const uint8_t *d_valid, int64_t n_groups, int32_t group_size,
+                          float *d_out, double *d_reward, spb_stream stream);
+
+/* ------------------------------------------------------------------------
+ * K5 sample_paths.  Replaces Sampling.random_sample + generate_scanpath
+ * (models/sampling.py:16-77) for K independent samples per image.
+ *   d_probs [N,T,A] f32, d_mu, d_sigma2 [N,T] f32 (decoder outputs)
+ *   d_q [K,N,T,A] f32 or NULL: injected Exp(1) draws of the categorical race
+ *   d_z [K,N,T]   f32 or NULL: injected N(0,1) draws of the duration
+ *   (NULL -> Philox4x32-10 streams from `seed`)
+ * out, all [K,N,T] unless noted:
+ *   d_actions i32, d_sel_prob f32 (gathered from the UNMASKED probs), d_dur f32,
+ *   d_action_mask, d_duration_mask f32, d_length [K,N] f32 (scanpath_length quirk kept),
+ *   d_xyd [K*N, T, 3] f64 (x px, y px, duration s) + d_len [K*N] i32: the predicted
+ *   scanpaths truncated at the first stop action, ready for spb_prep_paths.            */
+typedef struct spb_sample_geom {
+    int32_t map_width, map_height; /* 40 x 30 action map */
+    int32_t width, height;         /* 320 x 240 image */
+    int32_t min_length;            /* first min_length steps cannot stop (sampling.py:20) */
+    int32_t reserved;
+} spb_sample_geom;
+
+int spb_sample_paths(const float *d_probs, const float *d_mu, const float *d_sigma2, const float *d_q,
+                     const float *d_z, uint64_t seed, int32_t N, int32_t T, int32_t A, int32_t K,
+                     const spb_sample_geom *geom, int32_t *d_actions, float *d_sel_prob, float *d_dur,
+                     float *d_action_mask, float *d_duration_mask, float *d_length, double *d_xyd,
+                     int32_t *d_len, spb_stream stream);
+
+/* generate_scanpath alone (models/sampling.py:48-77) for given actions / durations
+ * [n_samples, T]: masks, scanpath_length and the packed scanpaths as above. */
+int spb_generate_scanpaths(const int32_t *d_actions, const float *d_dur, int64_t n_samples, int32_t T,
+                           const spb_sample_geom *geom, float *d_action_mask, float *d_duration_mask,
+                           float *d_length, double *d_xyd, int32_t *d_len, spb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANPATHS_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of libscanpaths_b200.so (the C ABI of include/scanpaths_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this
+raises.  PyTorch is only used by callers for device memory and streams; the
+library itself has no torch dependency.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libscanpaths_b200.so")
+
+
+class SpbError(RuntimeError):
+    pass
+
+
+class ScanMatchCfg(C.Structure):
+    _fields_ = [("Xres", C.c_int32), ("Yres", C.c_int32), ("Xbin", C.c_int32), ("Ybin", C.c_int32),
+                ("Threshold", C.c_double), ("GapValue", C.c_double), ("TempBin", C.c_double),
+                ("OffsetX", C.c_double), ("OffsetY", C.c_double)]
+
+
+class ScoreCfg(C.Structure):
+    _fields_ = [("sm", ScanMatchCfg),
+                ("sed_height", C.c_int32), ("sed_width", C.c_int32), ("sed_n", C.c_int32), ("reserved", C.c_int32),
+                ("stde_max_dim", C.c_double), ("dur_scale", C.c_double), ("max_sub", C.c_double),
+                ("d_sub_delta", C.c_void_p), ("d_xlut", C.c_void_p), ("d_ylut", C.c_void_p)]
+
+
+class PathPack(C.Structure):
+    _fields_ = [("d_sym", C.c_void_p), ("d_run", C.c_void_p), ("d_nwd", C.c_void_p), ("d_sed", C.c_void_p),
+                ("d_xyn", C.c_void_p), ("d_len", C.c_void_p), ("n_paths", C.c_int64), ("lmax", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class SampleGeom(C.Structure):
+    _fields_ = [("map_width", C.c_int32), ("map_height", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("min_length", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/scanpaths_b200.h declares: name -> (restype, argtypes)
+P, I32, I64, U64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+SYMBOLS = {
+    "spb_version": (C.c_int, []),
+    "spb_last_error": (C.c_char_p, []),
+    "spb_scanmatch_tables": (C.c_int, [C.POINTER(ScanMatchCfg), P, P, P, P, P]),
+    "spb_prep_paths": (C.c_int, [P, P, I64, I32, C.POINTER(ScoreCfg), P, P, P, P, P, P]),
+    "spb_score_workspace_bytes": (I64, [I64]),
+    "spb_score_pairs": (C.c_int, [C.POINTER(PathPack), C.POINTER(PathPack), P, P, I64, C.POINTER(ScoreCfg), P, P,
+                                  I64, P, P]),
+    "spb_reduce_pairs_eval": (C.c_int, [P, P, I64, I32, P, P, P]),
+    "spb_sample_paths": (C.c_int, [P, P, P, P, P, U64, I32, I32, I32, I32, C.POINTER(SampleGeom), P, P, P, P, P, P,
+                                   P, P, P]),
+    "spb_generate_scanpaths": (C.c_int, [P, P, I64, I32, C.POINTER(SampleGeom), P, P, P, P, P, P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (building is __graft_entry__.build()'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpbError("libscanpaths_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().spb_last_error().decode("utf-8", "replace")
+        raise SpbError("%s failed with status %d: %s" % (what or "scanpaths_b200 call", status, msg))
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous torch tensor / numpy array, or NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        if not t.is_contiguous():
+            raise SpbError("non-contiguous tensor passed to the C ABI")
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise SpbError("scanpaths_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

@@ -1,0 +1,198 @@
+"""Batched scoring on the GPU: packed scanpaths -> (ScanMatch-wd, ScanMatch-wod, SED, STDE).
+
+Host side of kernels K1-K4 (csrc/prep.cu, csrc/score_pairs.cu).  The mirror
+modules under ``scanpaths_b200.utils`` (reference names and signatures) are thin
+wrappers over this file.  torch is used for device memory and the stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# evaluation.py:159-162 -- the configuration every driver of the reference uses
+EVAL_SCANMATCH = dict(Xres=320, Yres=240, Xbin=16, Ybin=12, Offset=(0, 0), Threshold=3.5)
+EVAL_TEMPBIN = 50
+EVAL_STIMULUS = (240, 320, 3)
+
+
+class ScoreConfig:
+    """ScanMatch tables + SED / STDE geometry, resident on one device."""
+
+    def __init__(self, Xres=1024, Yres=768, Xbin=8, Ybin=6, Threshold=3.5, GapValue=0.0, TempBin=0.0,
+                 Offset=(0, 0), stimulus_shape=EVAL_STIMULUS, sed_n=5, dur_scale=1.0, device=None):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.sm = _lib.ScanMatchCfg(int(Xres), int(Yres), int(Xbin), int(Ybin), float(Threshold), float(GapValue),
+                                    float(TempBin), float(Offset[0]), float(Offset[1]))
+        nb = int(Xbin) * int(Ybin)
+        self.sub_delta = np.zeros(nb, dtype=np.float64)
+        self.xlut = np.zeros(int(Xres), dtype=np.uint8)
+        self.ylut = np.zeros(int(Yres), dtype=np.uint8)
+        mx = C.c_double(0.0)
+        _lib.check(lib.spb_scanmatch_tables(C.byref(self.sm), _lib.ptr(self.sub_delta), None, _lib.ptr(self.xlut),
+                                            _lib.ptr(self.ylut), C.byref(mx)), "spb_scanmatch_tables")
+        self.max_sub = mx.value
+        self.d_sub_delta = torch.from_numpy(self.sub_delta).to(self.device)
+        self.d_xlut = torch.from_numpy(self.xlut).to(self.device)
+        self.d_ylut = torch.from_numpy(self.ylut).to(self.device)
+        h, w = int(stimulus_shape[0]), int(stimulus_shape[1])
+        self.cfg = _lib.ScoreCfg(self.sm, h, w, int(sed_n), 0, float(max(stimulus_shape)), float(dur_scale),
+                                 self.max_sub, self.d_sub_delta.data_ptr(), self.d_xlut.data_ptr(),
+                                 self.d_ylut.data_ptr())
+
+    @classmethod
+    def evaluation(cls, device=None, dur_scale=1000.0):
+        """The drivers' configuration: 320x240, 16x12 bins, TempBin 50 ms, durations given in seconds."""
+        return cls(TempBin=EVAL_TEMPBIN, stimulus_shape=EVAL_STIMULUS, dur_scale=dur_scale, device=device,
+                   **EVAL_SCANMATCH)
+
+    def full_sub_matrix(self):
+        nb = self.sm.Xbin * self.sm.Ybin
+        full = np.zeros((nb, nb), dtype=np.float64)
+        _lib.check(_lib.load().spb_scanmatch_tables(C.byref(self.sm), None, _lib.ptr(full), None, None, None),
+                   "spb_scanmatch_tables")
+        return full
+
+
+@dataclass
+class PathPack:
+    """Symbol pack of n scanpaths (output of K1), all tensors on the GPU."""
+    xyd: torch.Tensor      # [n, lmax, 3] f64 (x, y, duration)
+    len: torch.Tensor      # [n] i32
+    sym: torch.Tensor      # [n, lmax] u8
+    run: torch.Tensor      # [n, lmax] i32
+    nwd: torch.Tensor      # [n] i32
+    sed: torch.Tensor      # [n, lmax] i32
+    xyn: torch.Tensor      # [n, lmax, 2] f64
+
+    @property
+    def n(self):
+        return self.xyd.shape[0]
+
+    @property
+    def lmax(self):
+        return self.xyd.shape[1]
+
+    def c_struct(self):
+        return _lib.PathPack(self.sym.data_ptr(), self.run.data_ptr(), self.nwd.data_ptr(), self.sed.data_ptr(),
+                             self.xyn.data_ptr(), self.len.data_ptr(), self.n, self.lmax, 0)
+
+
+def pad_paths(paths, lmax=None):
+    """list of [L,3] arrays -> (padded [n,lmax,3] f64 numpy, lengths i32 numpy)."""
+    n = len(paths)
+    lens = np.array([len(p) for p in paths], dtype=np.int32)
+    lmax = int(lmax or max(1, int(lens.max()) if n else 1))
+    out = np.zeros((n, lmax, 3), dtype=np.float64)
+    for i, p in enumerate(paths):
+        if len(p):
+            out[i, :len(p)] = np.asarray(p, dtype=np.float64).reshape(-1, 3)
+    return out, lens
+
+
+def structured_to_xyd(fix_vector):
+    """Reference structured array (start_x, start_y, duration) -> [L,3] f64."""
+    if len(fix_vector) == 0:
+        return np.zeros((0, 3), dtype=np.float64)
+    if getattr(fix_vector, "dtype", None) is not None and fix_vector.dtype.names:
+        names = fix_vector.dtype.names
+        return np.stack([fix_vector[names[0]], fix_vector[names[1]], fix_vector[names[2]]], 1).astype(np.float64)
+    return np.array([list(r) for r in list(fix_vector)], dtype=np.float64)
+
+
+def prep_paths(xyd: torch.Tensor, lens: torch.Tensor, cfg: ScoreConfig) -> PathPack:
+    """K1: xyd [n,lmax,3] f64 + lens [n] i32 (device tensors) -> PathPack."""
+    lib = _lib.load()
+    assert xyd.dtype == torch.float64 and lens.dtype == torch.int32 and xyd.is_cuda and lens.is_cuda
+    xyd = xyd.contiguous()
+    lens = lens.contiguous()
+    n, lmax = xyd.shape[0], xyd.shape[1]
+    dev = xyd.device
+    pack = PathPack(xyd, lens,
+                    torch.empty((n, lmax), dtype=torch.uint8, device=dev),
+                    torch.empty((n, lmax), dtype=torch.int32, device=dev),
+                    torch.empty((n,), dtype=torch.int32, device=dev),
+                    torch.empty((n, lmax), dtype=torch.int32, device=dev),
+                    torch.empty((n, lmax, 2), dtype=torch.float64, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(lib.spb_prep_paths(_lib.ptr(xyd), _lib.ptr(lens), n, lmax, C.byref(cfg.cfg), _lib.ptr(pack.sym),
+                                      _lib.ptr(pack.run), _lib.ptr(pack.nwd), _lib.ptr(pack.sed), _lib.ptr(pack.xyn),
+                                      _lib.current_stream()), "spb_prep_paths")
+    return pack
+
+
+def pack_paths(paths, cfg: ScoreConfig, lmax=None) -> PathPack:
+    """Host lists of [L,3] arrays -> device PathPack (one H2D copy + K1)."""
+    arr, lens = pad_paths(paths, lmax)
+    return prep_paths(torch.from_numpy(arr).to(cfg.device), torch.from_numpy(lens).to(cfg.device), cfg)
+
+
+class Workspace:
+    """Boundary-column workspace for with-duration strings longer than 256 symbols."""
+
+    def __init__(self, max_human_nwd: int, device):
+        nbytes = _lib.load().spb_score_workspace_bytes(int(max_human_nwd))
+        self.buf = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=device)
+        self.nbytes = nbytes
+
+
+def score_pairs(human: PathPack, sim: PathPack, pair_h: torch.Tensor, pair_s: torch.Tensor, cfg: ScoreConfig,
+                workspace: Workspace | None = None, out: torch.Tensor | None = None, check: bool = True):
+    """K2-K4.  pair_h / pair_s: i32 device tensors [P] indexing `human` / `sim`.
+    Returns scores [P,4] f64 on the device = (SM-wd, SM-wod, SED, STDE).
+    `workspace=None` sizes one from the packs (costs a device->host read of the
+    string lengths); pass a Workspace to stay asynchronous.  With `check`, a
+    too-small workspace raises instead of leaving NaNs."""
+    lib = _lib.load()
+    assert pair_h.dtype == torch.int32 and pair_s.dtype == torch.int32
+    P = pair_h.numel()
+    dev = pair_h.device
+    if out is None:
+        out = torch.empty((P, 4), dtype=torch.float64, device=dev)
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if workspace is None and P > 0 and sim.n > 0 and int(sim.nwd.max().item()) > 256:
+        workspace = Workspace(int(human.nwd.max().item()), dev)
+    hp, sp = human.c_struct(), sim.c_struct()
+    with torch.cuda.device(dev):
+        _lib.check(lib.spb_score_pairs(C.byref(hp), C.byref(sp), _lib.ptr(pair_h.contiguous()),
+                                       _lib.ptr(pair_s.contiguous()), P, C.byref(cfg.cfg), _lib.ptr(out),
+                                       _lib.ptr(workspace.buf) if workspace else None,
+                                       workspace.nbytes if workspace else 0, _lib.ptr(err), _lib.current_stream()),
+                   "spb_score_pairs")
+    if check and workspace is not None and int(err.item()) != 0:
+        raise _lib.SpbError("spb_score_pairs: workspace too small for the with-duration strings")
+    return out
+
+
+def reduce_pairs_eval(scores: torch.Tensor, group_size: int, valid: torch.Tensor | None = None):
+    """a7: scores [G*group_size, 4] -> (table [G,11] f32, reward [G] f64)."""
+    lib = _lib.load()
+    G = scores.shape[0] // group_size
+    dev = scores.device
+    out = torch.empty((G, 11), dtype=torch.float32, device=dev)
+    reward = torch.empty((G,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spb_reduce_pairs_eval(_lib.ptr(scores.contiguous()),
+                                             _lib.ptr(valid.contiguous()) if valid is not None else None, G,
+                                             group_size, _lib.ptr(out), _lib.ptr(reward), _lib.current_stream()),
+                   "spb_reduce_pairs_eval")
+    return out, reward
+
+
+def grid_pairs(n_images: int, k_samples: int, n_subjects: int, device):
+    """Pair map of the evaluation drivers for sample-major predictions
+    (sim index = k * n_images + image, as test.py:124-131 extends its lists) and
+    image-major humans (human index = image * n_subjects + s):
+    pair order = (k, image, s), i.e. `for pred: for subject` (evaluation.py:166-170)."""
+    sim = torch.arange(k_samples * n_images, device=device, dtype=torch.int32)
+    img = sim % n_images
+    s = torch.arange(n_subjects, device=device, dtype=torch.int32)
+    pair_s = sim[:, None].expand(-1, n_subjects).reshape(-1).contiguous()
+    pair_h = (img[:, None] * n_subjects + s[None, :]).reshape(-1).contiguous()
+    return pair_h, pair_s

@@ -1,0 +1,176 @@
+"""Drop-in for the reference's evaluation drivers on the GPU.
+
+Mirrors (names, arguments, return types):
+  evaluation, human_evaluation, pairs_eval   OSIE/utils/evaluation.py:11-340
+  pairs_eval_scanmatch                       COCO_Search18/utils/evaluation.py:313-352
+Every (human, prediction) pair of the call is scored by ONE launch of
+csrc/score_pairs.cu instead of the reference's triple Python loop.  MultiMatch
+(external multimatch-gaze 0.1.2, not part of this path) is not computed: its
+five slots are NaN, but its NaN rule (either scanpath shorter than 3 fixations)
+still drops rows exactly where the reference's aggregation drops them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import scoring as S
+
+MIN_LEN_VALID = 3   # multimatch_gaze.docomparison returns NaN below this
+
+_cfg = {}
+
+
+def _eval_cfg(device=None):
+    key = str(device)
+    if key not in _cfg:
+        _cfg[key] = S.ScoreConfig.evaluation(device=device, dur_scale=1000.0)
+    return _cfg[key]
+
+
+def _nan5():
+    return {"vector": np.nan, "direction": np.nan, "length": np.nan, "position": np.nan, "duration": np.nan}
+
+
+def _pack_humans(gt_fix_vectors, cfg):
+    """Packs each distinct subject list once (test.py:125 re-appends the same list
+    objects for every trial).  Returns (pack, first human index per entry, S per entry)."""
+    seen, paths, base, sizes = {}, [], [], []
+    for gts in gt_fix_vectors:
+        key = id(gts)
+        if key not in seen:
+            seen[key] = len(paths)
+            paths.extend(S.structured_to_xyd(g) for g in gts)
+        base.append(seen[key]); sizes.append(len(gts))
+    return S.pack_paths(paths, cfg), np.array(base, dtype=np.int64), np.array(sizes, dtype=np.int64)
+
+
+def _score_lists(gt_fix_vectors, predict_fix_vectors, device=None):
+    cfg = _eval_cfg(device)
+    preds = []
+    for p in predict_fix_vectors:
+        a = S.structured_to_xyd(p)
+        if len(a) == 0:
+            raise IndexError("too many indices for array: empty predicted scanpath")   # evaluation.py:181-183
+        preds.append(a)
+    hpack, base, sizes = _pack_humans(gt_fix_vectors, cfg)
+    ppack = S.pack_paths(preds, cfg)
+    pair_s = np.repeat(np.arange(len(preds), dtype=np.int64), sizes)
+    offs = np.concatenate([np.arange(s) for s in sizes]) if len(sizes) else np.zeros(0, np.int64)
+    pair_h = np.repeat(base, sizes) + offs
+    dev = cfg.device
+    scores = S.score_pairs(hpack, ppack, torch.from_numpy(pair_h.astype(np.int32)).to(dev),
+                           torch.from_numpy(pair_s.astype(np.int32)).to(dev), cfg)
+    return scores, hpack, ppack, pair_h, pair_s, sizes
+
+
+def _metric_dicts(scores, last_group):
+    """Aggregation of evaluation.py:211-280 from the [P,4] table (device, f64)."""
+    wd, wod = scores[:, 0], scores[:, 1]
+    sed = scores[:, 2].reshape(-1, last_group)
+    stde = scores[:, 3].reshape(-1, last_group)
+    f = lambda t: float(t.item())
+    std = lambda t: f(t.std(unbiased=False))
+    m = {"MultiMatch": _nan5(),
+         "ScanMatch": {"w/o duration": f(wod.mean()), "with duration": f(wd.mean())},
+         "VAME": {"SED": f(sed.mean()), "STDE": f(stde.mean()),
+                  "SED_best": f(sed.min(-1)[0].mean()), "STDE_best": f(stde.max(-1)[0].mean())}}
+    s = {"MultiMatch": _nan5(),
+         "ScanMatch": {"w/o duration": std(wod), "with duration": std(wd)},
+         "VAME": {"SED": std(sed), "STDE": std(stde),
+                  "SED_best": std(sed.min(-1)[0]), "STDE_best": std(stde.max(-1)[0])}}
+    return m, s
+
+
+def _per_group_means(scores, sizes):
+    sc = scores.cpu().numpy()
+    out, o = [], 0
+    for s in sizes:
+        out.append([np.nan] * 5 + list(sc[o:o + s].mean(axis=0)))
+        o += s
+    return out
+
+
+def evaluation(gt_fix_vectors, predict_fix_vectors, is_eliminating_nan=True):
+    """OSIE/utils/evaluation.py:151-282."""
+    scores, _, _, _, _, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    m, s = _metric_dicts(scores, int(sizes[-1]))
+    return m, s, _per_group_means(scores, sizes)
+
+
+def human_evaluation(dataloader):
+    """OSIE/utils/evaluation.py:11-148: all ordered pairs (i, j != i) of each image's
+    subjects; i plays the human, j the simulated scanpath."""
+    cfg = _eval_cfg()
+    paths, pair_h, pair_s, sizes, names = [], [], [], [], []
+    last_S = 0
+    for batch in dataloader:
+        names.extend(batch["img_names"])
+        for fix_vectors in batch["fix_vectors"]:
+            b = len(paths)
+            paths.extend(S.structured_to_xyd(f) for f in fix_vectors)
+            n = len(fix_vectors)
+            for i in range(n):
+                for j in range(n):
+                    if i != j:
+                        pair_h.append(b + i); pair_s.append(b + j)
+            sizes.append(n * (n - 1)); last_S = n
+    pack = S.pack_paths(paths, cfg)
+    dev = cfg.device
+    scores = S.score_pairs(pack, pack, torch.tensor(pair_h, dtype=torch.int32, device=dev),
+                           torch.tensor(pair_s, dtype=torch.int32, device=dev), cfg)
+    m, s = _metric_dicts(scores, last_S - 1)
+    per = _per_group_means(scores, sizes)
+    return m, s, {name: sc for name, sc in zip(names, per)}
+
+
+def pairs_eval(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None, ScanMatchwithoutDuration=None,
+               is_eliminating_nan=True):
+    """OSIE/utils/evaluation.py:284-340 -> [N, 11] (float32 values).  The two ScanMatch
+    arguments are accepted for signature compatibility; the drivers' fixed
+    configuration (train.py:201-203) is used."""
+    scores, hpack, ppack, pair_h, pair_s, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    S_ = int(sizes[0]) if len(sizes) else 0
+    if len(sizes) and not np.all(sizes == S_):
+        return _pairs_eval_ragged(scores, hpack, ppack, pair_h, pair_s, sizes, is_eliminating_nan)
+    dev = scores.device
+    ph = torch.from_numpy(pair_h).to(dev); ps = torch.from_numpy(pair_s).to(dev)
+    valid = ((hpack.len.long()[ph] >= MIN_LEN_VALID) & (ppack.len.long()[ps] >= MIN_LEN_VALID)).to(torch.uint8)
+    table, _ = S.reduce_pairs_eval(scores, S_, valid if is_eliminating_nan else valid)
+    out = table.cpu().numpy().astype(np.float64)
+    if not is_eliminating_nan:      # a NaN row poisons the sums in the reference (:326-335)
+        bad = (valid.reshape(-1, S_) == 0).any(1).cpu().numpy()
+        out[bad] = np.nan
+    return out
+
+
+def _pairs_eval_ragged(scores, hpack, ppack, pair_h, pair_s, sizes, is_eliminating_nan):
+    sc = scores.cpu().numpy()
+    hl, pl = hpack.len.cpu().numpy(), ppack.len.cpu().numpy()
+    out, o = [], 0
+    for s in sizes:
+        rows = sc[o:o + s]
+        ok = (hl[pair_h[o:o + s]] >= MIN_LEN_VALID) & (pl[pair_s[o:o + s]] >= MIN_LEN_VALID) & ~np.isnan(rows.sum(1))
+        v = np.full(11, np.nan)
+        if ok.any() and (is_eliminating_nan or ok.all()):
+            r = rows[ok]
+            v[5], v[6], v[7], v[8] = (r[:, 1].sum() / s, r[:, 0].sum() / s, r[:, 2].sum() / s, r[:, 3].sum() / s)
+            v[9], v[10] = r[:, 2].min(), r[:, 3].max()
+            v = v.astype(np.float32).astype(np.float64)
+        out.append(v); o += s
+    return np.array(out)
+
+
+def pairs_eval_scanmatch(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None,
+                         ScanMatchwithoutDuration=None, is_eliminating_nan=True):
+    """COCO_Search18/utils/evaluation.py:313-352 -> [N, 2] = (SM w/o duration, SM with duration)."""
+    scores, _, _, _, _, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    sc = scores[:, :2].cpu().numpy()
+    out, o = [], 0
+    for s in sizes:
+        rows = sc[o:o + s][:, ::-1]                       # (wod, wd)
+        if is_eliminating_nan:
+            rows = rows[~np.isnan(rows.sum(axis=1))]
+        out.append(rows.sum(axis=0) / s if rows.shape[0] else np.array([np.nan] * 2))
+        o += s
+    return np.array(out)
