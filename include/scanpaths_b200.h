@@ -163,6 +163,74 @@ int spb_generate_scanpaths(const int32_t *d_actions, const float *d_dur, int64_t
                            const spb_sample_geom *geom, float *d_action_mask, float *d_duration_mask,
                            float *d_length, double *d_xyd, int32_t *d_len, spb_stream stream);
 
+/* ------------------------------------------------------------------------
+ * K6/K7 decode: the 16-step ConvLSTM rollout + prediction head for a wave of
+ * images, everything after the once-per-image encoder.  Replaces
+ * baseline.inference from `state = init_hidden` on
+ * (OSIE/models/baseline_attention.py:333-396; AiR/models/baseline_attention.py:392-491;
+ * COCO_Search18/models/baseline_attention_multihead.py:339-405) incl. ConvLSTM.forward
+ * (:33-48), predict_head.forward (:141-166), the feedback features (:226-236) and the
+ * spatial / semantic memory attention (:69-80, :103-116).
+ *
+ * Weights are passed in PREPARED device layouts (scanpaths_b200/models/
+ * baseline_attention.py::prepare_weights builds them from a reference state_dict):
+ *   conv weights  fp16 pairs (hi, lo): w * scale = hi + lo / 2^11, rows = output
+ *                 channel, K index = (ky*ks + kx)*512 + ci; gate matrices have 2048
+ *                 rows ordered [channel block of 64][gate i,f,o,g][64].
+ * ---------------------------------------------------------------------- */
+typedef struct spb_decoder_weights {
+    const void *wx_hi, *wx_lo;       /* fp16 [2048, 4608]  lstm.*_x                     */
+    const void *wh_hi, *wh_lo;       /* fp16 [2048, 4608]  lstm.*_h                     */
+    const void *wp_hi, *wp_lo;       /* fp16 [n_weight_sets*512, 12800]  5x5 layer(s)   */
+    const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
+    const float *bias_p;             /* [n_weight_sets*512]                              */
+    const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */
+                                     /*   row ((s*3+g)*512+co)*9+tap, col ci             */
+    const float *w2, *w3;            /* [512] object_head.sal_layer_2 / sal_layer_3      */
+    const float *wd1;                /* [49, 512] object_head.drt_layer_1, tap-major     */
+    const float *wd2;                /* [2, 48]   object_head.drt_layer_2                */
+    const float *w_spatial_embed;    /* [1200, 1200] */
+    const float *b_spatial_embed;    /* [1200] */
+    const float *w_semantic_embed;   /* [512, 512] */
+    const float *b_semantic_embed;   /* [512] */
+    const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
+    const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
+    float b2, b3, bd1, bd2_mu, bd2_sigma;
+    float inv_scale_x, inv_scale_h, inv_scale_p;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
+    int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
+    int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
+    int32_t reserved;
+} spb_decoder_weights;
+
+typedef struct spb_decoder_io {
+    int32_t n_images, steps;
+    int32_t use_tensor_cores;        /* 1: tcgen05 implicit GEMM; 0: SIMT fp32 verification kernel */
+    int32_t reserved;
+    const float *d_vf;               /* [N, 512, 30, 40] visual_feature (NCHW, as the encoder emits it) */
+    const float *d_att;              /* [N, 1200] initial attention map, or NULL = zeros (OSIE)         */
+    const int32_t *d_w_row_base;     /* [N] first row of the 5x5 weight set of each image (task*512), or NULL */
+    void *d_workspace;               /* spb_decoder_workspace_bytes() bytes, 1024-byte aligned */
+    int64_t workspace_bytes;
+    float *d_probs;                  /* [n_heads, N, steps, 1201] */
+    float *d_mu, *d_sigma2;          /* [n_heads, N, steps] */
+    float *d_action_map;             /* [n_heads, N, steps, 1200] */
+} spb_decoder_io;
+
+int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t n_heads, int32_t steps);
+int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream);
+
+/* One implicit-GEMM convolution on its own (unit tests / profiling of the hot kernel):
+ * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]. */
+int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, const void *d_w_lo,
+                  const int32_t *d_w_row_base, int64_t w_rows, const float *d_bias, float *d_out, int64_t ldo,
+                  int32_t n_images, int32_t cols, int32_t ks, float inv_scale, int32_t use_tensor_cores,
+                  spb_stream stream);
+
+/* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11; NCHW [N,C,HW] -> NHWC when `transpose`. */
+int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
+                   int32_t transpose, float scale, spb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

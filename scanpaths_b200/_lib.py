@@ -57,6 +57,33 @@ SYMBOLS = {
     "spb_generate_scanpaths": (C.c_int, [P, P, I64, I32, C.POINTER(SampleGeom), P, P, P, P, P, P]),
 }
 
+
+class DecoderWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("wx_hi", "wx_lo", "wh_hi", "wh_lo", "wp_hi", "wp_lo", "bias_gate", "bias_p", "wm", "w2", "w3", "wd1",
+                 "wd2", "w_spatial_embed", "b_spatial_embed", "w_semantic_embed", "b_semantic_embed",
+                 "w_eff_spatial", "u_semantic")] + \
+               [(n, C.c_float) for n in ("b2", "b3", "bd1", "bd2_mu", "bd2_sigma", "inv_scale_x", "inv_scale_h",
+                                         "inv_scale_p")] + \
+               [(n, C.c_int32) for n in ("n_streams", "n_heads", "n_weight_sets", "reserved")]
+
+
+class DecoderIO(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("steps", C.c_int32), ("use_tensor_cores", C.c_int32),
+                ("reserved", C.c_int32), ("d_vf", C.c_void_p), ("d_att", C.c_void_p), ("d_w_row_base", C.c_void_p),
+                ("d_workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("d_probs", C.c_void_p),
+                ("d_mu", C.c_void_p), ("d_sigma2", C.c_void_p), ("d_action_map", C.c_void_p)]
+
+
+SYMBOLS.update({
+    "spb_decoder_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "spb_decode": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderIO), C.c_void_p]),
+    "spb_conv_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                                   C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "spb_split_fp16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_float, C.c_void_p]),
+})
+
 _lib = None
 
 

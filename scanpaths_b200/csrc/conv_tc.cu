@@ -1,0 +1,302 @@
+// Implicit-GEMM 3x3 / 5x5 convolution on Blackwell tensor cores (tcgen05 + TMEM + TMA).
+//
+// out[(img*1200 + p)*ldo + col] = inv_scale * sum_{tap,ci} a[img, p+tap, ci] * w[row(col), tap, ci] (+ bias)
+//
+// This is the dominant kernel of the decode path: the 3x3 gate convolutions of the
+// ConvLSTM (ConvLSTM.forward, OSIE/models/baseline_attention.py:39-42; M = 1200 pixels per
+// image, N = 2048 = 4 gates x 512, K = 9 x 512) and the 5x5 layer before the head
+// (:202, :352; N = 512, K = 25 x 512).
+//
+// Design
+//   * one CTA per (120-pixel, 256-column) output tile: 120 = 3 image rows x 40, so every
+//     filter tap of the A operand is ONE 4-D TMA box {64 ch, 40 w, 3 h, 1 img} shifted by the
+//     tap offset; out-of-image rows / columns are zero-filled by TMA (the conv padding).
+//     The UMMA tile is 128 x 256; its last 8 rows are don't-care.
+//   * fp32-equivalent arithmetic on the fp16 pipe: every operand is a pair
+//     x = hi + lo / 2^11 (11 + 11 significand bits).  Three MMAs per k-step:
+//     hi*hi -> accumulator 0, hi*lo + lo*hi -> accumulator 1 (scaled by 2^11), combined in
+//     the epilogue.  The dropped lo*lo term is 2^-22 relative.  TMEM: 2 x 256 fp32 columns.
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator,
+//     warps 2-5 epilogue (tcgen05.ld 32 lanes x 16 columns -> scale/bias -> 64 B stores).
+//   * operands staged by TMA with 128-byte swizzle, K-major; kStages-deep mbarrier ring.
+#include <cuda.h>
+
+#include "decoder.cuh"
+
+namespace spb {
+
+namespace tc {
+
+constexpr int kBlockM = 128, kValidM = 120, kBlockN = 256, kBlockK = 64, kStages = 2;
+constexpr int kABytes = kBlockM * kBlockK * 2;            // 16 KB (15 KB written by TMA)
+constexpr int kATxBytes = kValidM * kBlockK * 2;          // 15360
+constexpr int kBBytes = kBlockN * kBlockK * 2;            // 32 KB
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;    // 96 KB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cf. cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups |
+// version 1 | layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    ConvGemmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bar0 + 8 * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8 * (kStages + s); };
+    const uint32_t tmem_full_bar = bar0 + 8 * (2 * kStages);
+    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y, img = blockIdx.z;
+    constexpr int kNumKB = KS * KS * (kE / kBlockK);
+    constexpr int kPad = KS / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + n_tile * kBlockN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            const int y0 = m_tile * 3;
+            for (int kb = 0; kb < kNumKB; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(empty_bar(s), ((kb / kStages) & 1) ^ 1);
+                const int tap = kb / (kE / kBlockK), cb = kb % (kE / kBlockK);
+                const int ky = tap / KS, kx = tap % KS;
+                const uint32_t sa = base + s * kStageBytes;
+                mbar_expect_tx(full_bar(s), 2 * kATxBytes + 2 * kBBytes);
+                tma_load_4d(sa, &tmA_hi, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
+                tma_load_4d(sa + kABytes, &tmA_lo, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
+                tma_load_2d(sa + 2 * kABytes, &tmB_hi, full_bar(s), kb * kBlockK, row_base);
+                tma_load_2d(sa + 2 * kABytes + kBBytes, &tmB_lo, full_bar(s), kb * kBlockK, row_base);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t d_main = tmem_base, d_corr = tmem_base + kBlockN;
+            for (int kb = 0; kb < kNumKB; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(full_bar(s), (kb / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + s * kStageBytes;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
+                const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                    umma_f16(d_main, a_hi + adv, b_hi + adv, acc);
+                    umma_f16(d_corr, a_hi + adv, b_lo + adv, acc);
+                    umma_f16(d_corr, a_lo + adv, b_hi + adv, 1u);
+                }
+                umma_commit(empty_bar(s));            // frees this smem stage once the MMAs have read it
+            }
+            umma_commit(tmem_full_bar);               // accumulators complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        const bool valid = r < kValidM;
+        const int64_t orow = ((int64_t)img * kHW + m_tile * kValidM + r) * a.ldo + n_tile * kBlockN;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < kBlockN; c += 16) {
+            uint32_t vm[16], vc[16];
+            tmem_ld16(lane_addr + c, vm);
+            tmem_ld16(lane_addr + kBlockN + c, vc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (valid) {
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = (__uint_as_float(vm[j]) + __uint_as_float(vc[j]) * (1.0f / kLoScale)) * a.inv_scale;
+                    if (a.bias) v += a.bias[row_base + c + j];
+                    o[j] = v;
+                }
+                float4 *dst = reinterpret_cast<float4 *>(a.out + orow + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images) {
+    const cuuint64_t dims[4] = {(cuuint64_t)kE, (cuuint64_t)kW, (cuuint64_t)kH, (cuuint64_t)n_images};
+    const cuuint64_t strides[3] = {(cuuint64_t)kE * 2, (cuuint64_t)kW * kE * 2, (cuuint64_t)kHW * kE * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kW, 3, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K) {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockN};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace tc
+
+int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
+    using namespace tc;
+    if (a.cols % kBlockN != 0 || (a.ldo % 4) != 0 || (a.ks != 3 && a.ks != 5)) {
+        set_error("conv_gemm_tc: cols must be a multiple of %d, ldo of 4, ks 3 or 5", kBlockN);
+        return SPB_ERR_ARG;
+    }
+    if (a.n_images > 65535) {
+        set_error("conv_gemm_tc: at most 65535 images per launch");
+        return SPB_ERR_ARG;
+    }
+    if (get_encode() == nullptr) {
+        set_error("conv_gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+        return SPB_ERR_CUDA;
+    }
+    const int64_t K = (int64_t)a.ks * a.ks * kE;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images);
+    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images);
+    if (!rc) rc = make_map_b(&mb_hi, a.w_hi, a.w_rows, K);
+    if (!rc) rc = make_map_b(&mb_lo, a.w_lo, a.w_rows, K);
+    if (rc) {
+        set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
+        return SPB_ERR_CUDA;
+    }
+    dim3 grid(a.cols / kBlockN, kHW / kValidM, a.n_images);
+    if (a.ks == 3) {
+        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        conv_gemm_tc_kernel<3><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+    } else {
+        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        conv_gemm_tc_kernel<5><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+    }
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
+}  // namespace spb

@@ -1,0 +1,661 @@
+// K6/K7 decode: the ConvLSTM rollout + prediction head for a wave of images.
+//
+// Restructured (not translated) from baseline.inference
+// (OSIE/models/baseline_attention.py:333-396 and the AiR / COCO variants):
+//   * the four x-convolutions are loop-invariant (x = visual_feature never changes,
+//     :350) and are evaluated once per image into `xg`;
+//   * the spatial (x) semantic convolutions (:36, :39-41) are rank-1:
+//     conv(W, s (x) m)[co,p] = sum_tap (sum_ci W[co,ci,tap] m[ci]) s[p+tap]
+//     -> one small GEMM per step (V) + 27 FMAs per output in the cell kernel;
+//   * in both memory attentions the "current" branch adds the same constant to every
+//     history entry's score and cancels in the softmax (:76-77, :111-113), and the
+//     list branch is linear, so each entry's score is one dot product with a
+//     precomputed vector (w_eff_spatial / u_semantic);
+//   * what remains per step are two dense implicit GEMMs -- 3x3 gates
+//     (M=1200, N=2048, K=4608) and the 5x5 layer (M=1200, N=512, K=12800) -- run on
+//     tcgen05 tensor cores by conv_tc.cu with fp16 (hi, lo) operand pairs
+//     (fp32-equivalent: the parity gate is 1e-5 on the per-step probabilities).
+// The small kernels here are the glue between those GEMMs; all of them are HBM- or
+// latency-bound and deterministic (no float atomics).
+#include <math.h>
+
+#include "decoder.cuh"
+
+namespace spb {
+
+// ---------------------------------------------------------------------------
+// fp32 -> fp16 (hi, lo) pairs; optional [C,HW] -> [HW,C] transpose per outer index
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split_one(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+}
+
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int C, int HW,
+                       float scale) {
+    __shared__ float tile[32][33];
+    const int64_t n = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + tx;
+        tile[r][tx] = (c < C && p < HW) ? x[(n * C + c) * HW + p] * scale : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + tx;
+        if (p < HW && c < C) {
+            __half h, l;
+            split_one(tile[tx][r], h, l);
+            hi[(n * HW + p) * C + c] = h;
+            lo[(n * HW + p) * C + c] = l;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_plain_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int64_t total,
+                   float scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        __half h, l;
+        split_one(x[i] * scale, h, l);
+        hi[i] = h; lo[i] = l;
+    }
+}
+
+// mean over channels of the feature map: vfmean[n,p] (loop-invariant part of get_spatial_semantic, :226-230)
+__global__ void __launch_bounds__(256)
+vfmean_kernel(const float *__restrict__ vf, float *__restrict__ vfmean, int64_t n_images) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n_images * kHW) return;
+    const int64_t n = idx / kHW;
+    const int p = (int)(idx - n * kHW);
+    float s = 0.0f;
+    for (int c = 0; c < kE; ++c) s += vf[(n * kE + c) * kHW + p];
+    vfmean[idx] = s / (float)kE;
+}
+
+// ---------------------------------------------------------------------------
+// SIMT fp32 implicit-GEMM convolution on the same fp16 (hi, lo) operands as the
+// tensor-core kernel.  Verification path only (exact fp32 FMA accumulation).
+// 64 pixels x 64 columns per block, 4x4 per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_gemm_simt_kernel(ConvGemmArgs a) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int64_t m0 = (int64_t)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t M = (int64_t)a.n_images * kHW;
+    const int K = a.ks * a.ks * kE, pad = a.ks / 2;
+    float acc[4][4] = {};
+    // loader mapping: 64 rows x 16 k, 4 elements per thread
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    const int64_t gm = m0 + lr;
+    const bool mvalid = gm < M;
+    const int64_t img = mvalid ? gm / kHW : 0;
+    const int p = mvalid ? (int)(gm - img * kHW) : 0;
+    const int py = p / kW, px = p - py * kW;
+    const int wcol = n0 + lr;
+    const bool nvalid = wcol < a.cols;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const int tap = k0 / kE, ci0 = k0 - tap * kE + lk;
+        const int ky = tap / a.ks, kx = tap - ky * a.ks;
+        const int yy = py + ky - pad, xx = px + kx - pad;
+        float av[4] = {0, 0, 0, 0}, bv[4] = {0, 0, 0, 0};
+        if (mvalid && yy >= 0 && yy < kH && xx >= 0 && xx < kW) {
+            const int64_t off = ((img * kH + yy) * kW + xx) * kE + ci0;
+            for (int e = 0; e < 4; ++e)
+                av[e] = __half2float(a.a_hi[off + e]) + __half2float(a.a_lo[off + e]) * (1.0f / kLoScale);
+        }
+        if (nvalid) {
+            // all rows of one block belong to the image of its first pixel row only when w_row_base is
+            // NULL; otherwise resolve per output row below (done in the epilogue loop through `img`)
+            const int64_t base = a.w_row_base ? a.w_row_base[m0 / kHW] : 0;
+            const int64_t off = (base + wcol) * (int64_t)K + k0 + lk;
+            for (int e = 0; e < 4; ++e)
+                bv[e] = __half2float(a.w_hi[off + e]) + __half2float(a.w_lo[off + e]) * (1.0f / kLoScale);
+        }
+        __syncthreads();
+        for (int e = 0; e < 4; ++e) { As[lk + e][lr] = av[e]; Bs[lk + e][lr] = bv[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float ar[4], br[4];
+            for (int i = 0; i < 4; ++i) ar[i] = As[k][ty * 4 + i];
+            for (int j = 0; j < 4; ++j) br[j] = Bs[k][tx * 4 + j];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            if (col >= a.cols) continue;
+            const int64_t base = a.w_row_base ? a.w_row_base[m / kHW] : 0;
+            float v = acc[i][j] * a.inv_scale;
+            if (a.bias) v += a.bias[base + col];
+            a.out[m * a.ldo + col] = v;
+        }
+    }
+}
+
+int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s) {
+    // with per-image weight sets a block must not straddle two images: 1200 is not a multiple of 64,
+    // so launch per image in that case (verification path, speed is irrelevant)
+    if (a.w_row_base) {
+        for (int n = 0; n < a.n_images; ++n) {
+            ConvGemmArgs b = a;
+            b.n_images = 1;
+            b.a_hi += (int64_t)n * kHW * kE; b.a_lo += (int64_t)n * kHW * kE;
+            b.out += (int64_t)n * kHW * a.ldo;
+            b.w_row_base = a.w_row_base + n;
+            dim3 grid((kHW + 63) / 64, (a.cols + 63) / 64);
+            conv_gemm_simt_kernel<<<grid, 256, 0, s>>>(b);
+        }
+    } else {
+        const int64_t M = (int64_t)a.n_images * kHW;
+        dim3 grid((unsigned)((M + 63) / 64), (a.cols + 63) / 64);
+        conv_gemm_simt_kernel<<<grid, 256, 0, s>>>(a);
+    }
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C[M,N] = A[M,K] * B[N,K]^T + bias[N]   (fp32 SIMT; the small per-step GEMMs:
+// spatial_embed, semantic_embed, rank-1 gate projection)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
+                const float *__restrict__ bias, float *__restrict__ C, int64_t ldc, int M, int N, int K) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float av[4], bv[4];
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + lk + e;
+            av[e] = (m0 + lr < M && k < K) ? A[(int64_t)(m0 + lr) * lda + k] : 0.0f;
+            bv[e] = (n0 + lr < N && k < K) ? B[(int64_t)(n0 + lr) * ldb + k] : 0.0f;
+        }
+        __syncthreads();
+        for (int e = 0; e < 4; ++e) { As[lk + e][lr] = av[e]; Bs[lk + e][lr] = bv[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float ar[4], br[4];
+            for (int i = 0; i < 4; ++i) ar[i] = As[k][ty * 4 + i];
+            for (int j = 0; j < 4; ++j) br[j] = Bs[k][tx * 4 + j];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) C[(int64_t)m * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.0f);
+        }
+    }
+}
+
+static int sgemm_nt(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias, float *C, int64_t ldc,
+                    int M, int N, int K, cudaStream_t s) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    sgemm_nt_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// ConvLSTM cell (ConvLSTM.forward :39-46): gates from acc (h-conv) + xg (x-conv + biases)
+// + rank-1 memory term; c' = f c + i g; h' = o c' (no tanh on c).  One thread per
+// (image, pixel, channel); writes c in fp32 and h as the fp16 (hi, lo) pair the next
+// convolutions consume.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, const float *__restrict__ V,
+                 const float *__restrict__ sp_mem, float *__restrict__ c, __half *__restrict__ h_hi,
+                 __half *__restrict__ h_lo, int64_t n_images, int S) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n_images * kHW * kE) return;
+    const int ch = (int)(idx & (kE - 1));
+    const int64_t np = idx >> 9;
+    const int64_t n = np / kHW;
+    const int p = (int)(np - n * kHW);
+    const int py = p / kW, px = p - py * kW;
+    const int64_t g0 = np * kGateCols + (ch >> 6) * 256 + (ch & 63);
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pre[g] = xg[g0 + g * 64] + acc[g0 + g * 64];
+    for (int s = 0; s < S; ++s) {
+        const float *sp = sp_mem + (n * S + s) * kHW;
+        const float *v = V + ((n * S + s) * 3) * (int64_t)(kE * 9) + ch * 9;
+        float r[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = py + ky - 1, xx = px + kx - 1;
+                if (yy >= 0 && yy < kH && xx >= 0 && xx < kW) {
+                    const float sv = sp[yy * kW + xx];
+                    const int tap = ky * 3 + kx;
+                    r[0] = fmaf(v[tap], sv, r[0]);
+                    r[1] = fmaf(v[kE * 9 + tap], sv, r[1]);
+                    r[2] = fmaf(v[2 * kE * 9 + tap], sv, r[2]);
+                }
+            }
+        pre[0] += r[0]; pre[1] += r[1]; pre[2] += r[2];
+    }
+    const float gi = 1.0f / (1.0f + expf(-pre[0]));
+    const float gf = 1.0f / (1.0f + expf(-pre[1]));
+    const float go = 1.0f / (1.0f + expf(-pre[2]));
+    const float gg = tanhf(pre[3]);
+    const float cn = gf * c[idx] + gi * gg;
+    c[idx] = cn;
+    __half hh, hl;
+    split_one(go * cn, hh, hl);
+    h_hi[idx] = hh; h_lo[idx] = hl;
+}
+
+// ---------------------------------------------------------------------------
+// Head, part 1 (predict_head.forward :141-150): per pixel, the channel dot products of
+// feat with sal_layer_2, sal_layer_3 and with the <= 4 drt_layer_1 taps under which the
+// pixel falls (7x7 kernel, stride 5, pad 2 -> 6x8 windows).  One warp per (image, head, pixel).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_reduce_kernel(const float *__restrict__ feat, int HD, const float *__restrict__ w2, const float *__restrict__ w3,
+                   const float *__restrict__ wd1, float *__restrict__ y2, float *__restrict__ y3,
+                   float *__restrict__ dc, int64_t n_images) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_images * HD * kHW) return;
+    const int p = (int)(warp % kHW);
+    const int64_t nh = warp / kHW;
+    const int hd = (int)(nh % HD);
+    const int64_t n = nh / HD;
+    const int py = p / kW, px = p - py * kW;
+    const float *f = feat + (n * kHW + p) * (int64_t)(HD * kE) + hd * kE;
+    // window slots: a = 0 -> oy = (py+2)/5, a = 1 -> oy - 1 (valid when (py+2)%5 <= 1); same for x
+    int tapi[4];
+    {
+        const int qy = (py + 2) / 5, ry = (py + 2) % 5, qx = (px + 2) / 5, rx = (px + 2) % 5;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const int oy = qy - a, ox = qx - b, ky = ry + 5 * a, kx = rx + 5 * b;
+                const bool ok = oy >= 0 && oy < 6 && ox >= 0 && ox < 8 && ky < 7 && kx < 7;
+                tapi[a * 2 + b] = ok ? ky * 7 + kx : -1;
+            }
+    }
+    float s2 = 0.0f, s3 = 0.0f, sd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int cc = lane; cc < kE; cc += 32) {
+        const float v = f[cc];
+        s2 = fmaf(v, w2[cc], s2);
+        s3 = fmaf(v, w3[cc], s3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (tapi[q] >= 0) sd[q] = fmaf(v, wd1[tapi[q] * kE + cc], sd[q]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sd[q] += __shfl_xor_sync(0xffffffffu, sd[q], o);
+    }
+    if (lane == 0) {
+        y2[warp] = s2; y3[warp] = s3;
+        float4 o4 = make_float4(sd[0], sd[1], sd[2], sd[3]);
+        reinterpret_cast<float4 *>(dc)[warp] = o4;
+    }
+}
+
+__device__ __forceinline__ float block_reduce(float v, float *sh, bool is_max) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, u) : v + u;
+    }
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = sh[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+    return r;
+}
+
+// Head, part 2 (:144-166): stop logit, action map, softmax over the 1201 actions, duration
+// head, and the spatial feedback feature relu(map * mean_c(vf)) (:226-230, :359).
+// One block per (image, head).
+__global__ void __launch_bounds__(256)
+head_finish_kernel(const float *__restrict__ y2, const float *__restrict__ y3, const float *__restrict__ dc,
+                   const float *__restrict__ wd2, spb_decoder_weights w, const float *__restrict__ vfmean,
+                   float *__restrict__ sp_feat, float *__restrict__ probs, float *__restrict__ mu,
+                   float *__restrict__ sigma2, float *__restrict__ amap_out, int HD, int64_t n_images, int t,
+                   int steps) {
+    __shared__ float sh[8];
+    __shared__ float t1[48];
+    const int64_t nh = blockIdx.x;
+    const int hd = (int)(nh % HD);
+    const int64_t n = nh / HD;
+    const float *py2 = y2 + nh * kHW, *py3 = y3 + nh * kHW;
+    const int64_t orow = ((int64_t)hd * n_images + n) * steps + t;
+    float *pr = probs + orow * (kHW + 1);
+    float *am = amap_out + orow * kHW;
+    float s = 0.0f;
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) s += py2[p];
+    const float stop = block_reduce(s, sh, false) / (float)kHW + w.b2;
+    float mx = stop;
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) {
+        const float a = fmaxf(py3[p] + w.b3, 0.0f);
+        am[p] = a;
+        sp_feat[nh * kHW + p] = fmaxf(a * vfmean[n * kHW + p], 0.0f);
+        mx = fmaxf(mx, a);
+    }
+    mx = block_reduce(mx, sh, true);
+    float se = (threadIdx.x == 0) ? expf(stop - mx) : 0.0f;
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) se += expf(am[p] - mx);
+    se = block_reduce(se, sh, false);
+    if (threadIdx.x == 0) pr[0] = expf(stop - mx) / se;
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) pr[1 + p] = expf(am[p] - mx) / se;
+    // duration head: t1 = relu(conv7x7 s5 p2 + b), gathered from the per-pixel slot contributions
+    if (threadIdx.x < 48) {
+        const int oy = threadIdx.x / 8, ox = threadIdx.x % 8;
+        float a = 0.0f;
+        for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx) {
+                const int yy = 5 * oy - 2 + ky, xx = 5 * ox - 2 + kx;
+                if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
+                const int sa = ((yy + 2) / 5 == oy) ? 0 : 1, sb = ((xx + 2) / 5 == ox) ? 0 : 1;
+                a += dc[(nh * kHW + yy * kW + xx) * 4 + sa * 2 + sb];
+            }
+        t1[threadIdx.x] = fmaxf(a + w.bd1, 0.0f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.0f, v = 0.0f;
+        for (int o = 0; o < 48; ++o) { m = fmaf(wd2[o], t1[o], m); v = fmaf(wd2[48 + o], t1[o], v); }
+        mu[orow] = m + w.bd2_mu;
+        sigma2[orow] = expf(v + w.bd2_sigma);
+    }
+}
+
+// spatial feedback feature from an initial attention map (or zeros): relu(att * mean_c(vf)) (:335)
+__global__ void __launch_bounds__(256)
+init_spatial_feat_kernel(const float *__restrict__ att, const float *__restrict__ vfmean, float *__restrict__ sp_feat,
+                         int S, int64_t n_images) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n_images * S * kHW) return;
+    const int p = (int)(idx % kHW);
+    const int64_t n = idx / ((int64_t)S * kHW);
+    const float a = att ? att[n * kHW + p] : 0.0f;
+    sp_feat[idx] = fmaxf(a * vfmean[n * kHW + p], 0.0f);
+}
+
+// semantic feedback feature (get_channel_semantic :232-236, :362): relu(mean_p(map[p] vf[c,p])).
+// One warp per (image, channel); `maps` holds S maps per image with stride map_stride between
+// streams and image_stride between images (att: S identical copies via stride 0).
+__global__ void __launch_bounds__(256)
+semantic_feat_kernel(const float *__restrict__ vf, const float *__restrict__ maps, int64_t image_stride,
+                     int64_t stream_stride, int S, float *__restrict__ se_feat, int64_t n_images) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_images * kE) return;
+    const int64_t n = warp / kE;
+    const int c = (int)(warp - n * kE);
+    const float *row = vf + (n * kE + c) * kHW;
+    float s[2] = {0.0f, 0.0f};
+    for (int p = lane; p < kHW; p += 32) {
+        const float v = row[p];
+        for (int st = 0; st < S; ++st)
+            s[st] = fmaf(v, maps ? maps[n * image_stride + st * stream_stride + p] : 0.0f, s[st]);
+    }
+    for (int st = 0; st < S; ++st) {
+        float a = s[st];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) se_feat[(n * S + st) * kE + c] = fmaxf(a / (float)kHW, 0.0f);
+    }
+}
+
+// Memory attention update (spatial_att :103-116, semantic_att :69-80): append the new embedded
+// feature to the history, score it, softmax over the t+1 entries, weighted sum.
+// One block per (image, stream).
+__global__ void __launch_bounds__(256)
+attention_update_kernel(const float *__restrict__ sp_new, const float *__restrict__ se_new,
+                        const float *__restrict__ w_eff, const float *__restrict__ u_sem,
+                        float *__restrict__ sp_list, float *__restrict__ se_list, float *__restrict__ sp_score,
+                        float *__restrict__ se_score, float *__restrict__ sp_mem, float *__restrict__ se_mem, int t,
+                        int cap) {
+    __shared__ float sh[8];
+    __shared__ float wsp[32], wse[32];
+    const int64_t ns = blockIdx.x;
+    float *spl = sp_list + ns * (int64_t)cap * kHW, *sel = se_list + ns * (int64_t)cap * kE;
+    float a = 0.0f, b = 0.0f;
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) {
+        const float v = sp_new[ns * kHW + p];
+        spl[(int64_t)t * kHW + p] = v;
+        a = fmaf(v, w_eff[p], a);
+    }
+    for (int c = threadIdx.x; c < kE; c += blockDim.x) {
+        const float v = se_new[ns * kE + c];
+        sel[(int64_t)t * kE + c] = v;
+        b = fmaf(v, u_sem[c], b);
+    }
+    a = block_reduce(a, sh, false);
+    b = block_reduce(b, sh, false);
+    if (threadIdx.x == 0) { sp_score[ns * cap + t] = a; se_score[ns * cap + t] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m1 = -INFINITY, m2 = -INFINITY, d1 = 0.0f, d2 = 0.0f;
+        for (int j = 0; j <= t; ++j) { m1 = fmaxf(m1, sp_score[ns * cap + j]); m2 = fmaxf(m2, se_score[ns * cap + j]); }
+        for (int j = 0; j <= t; ++j) {
+            wsp[j] = expf(sp_score[ns * cap + j] - m1); d1 += wsp[j];
+            wse[j] = expf(se_score[ns * cap + j] - m2); d2 += wse[j];
+        }
+        for (int j = 0; j <= t; ++j) { wsp[j] /= d1; wse[j] /= d2; }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < kHW; p += blockDim.x) {
+        float s = 0.0f;
+        for (int j = 0; j <= t; ++j) s = fmaf(spl[(int64_t)j * kHW + p], wsp[j], s);
+        sp_mem[ns * kHW + p] = s;
+    }
+    for (int c = threadIdx.x; c < kE; c += blockDim.x) {
+        float s = 0.0f;
+        for (int j = 0; j <= t; ++j) s = fmaf(sel[(int64_t)j * kE + c], wse[j], s);
+        se_mem[ns * kE + c] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct Workspace {
+    __half *vf_hi, *vf_lo, *h_hi, *h_lo;
+    float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
+        *sp_score, *se_score, *sp_mem, *se_mem;
+    int64_t bytes;
+};
+
+static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
+    Workspace w;
+    int64_t o = 0;
+    auto take = [&](int64_t nbytes) {
+        void *p = base ? (void *)((char *)base + o) : nullptr;
+        o += (nbytes + 1023) & ~(int64_t)1023;
+        return p;
+    };
+    const int cap = steps + 1;
+    w.vf_hi = (__half *)take(N * kHW * kE * 2);
+    w.vf_lo = (__half *)take(N * kHW * kE * 2);
+    w.h_hi = (__half *)take(N * kHW * kE * 2);
+    w.h_lo = (__half *)take(N * kHW * kE * 2);
+    w.vfmean = (float *)take(N * kHW * 4);
+    w.xg = (float *)take(N * kHW * kGateCols * 4);
+    w.c = (float *)take(N * kHW * kE * 4);
+    w.acc = (float *)take(N * kHW * kGateCols * 4);
+    w.feat = (float *)take(N * kHW * HD * kE * 4);
+    w.V = (float *)take(N * S * 3 * kE * 9 * 4);
+    w.y2 = (float *)take(N * HD * kHW * 4);
+    w.y3 = (float *)take(N * HD * kHW * 4);
+    w.dc = (float *)take(N * HD * kHW * 16);
+    w.sp_feat = (float *)take(N * S * kHW * 4);
+    w.se_feat = (float *)take(N * S * kE * 4);
+    w.sp_new = (float *)take(N * S * kHW * 4);
+    w.se_new = (float *)take(N * S * kE * 4);
+    w.sp_list = (float *)take(N * S * cap * kHW * 4);
+    w.se_list = (float *)take(N * S * cap * kE * 4);
+    w.sp_score = (float *)take(N * S * cap * 4);
+    w.se_score = (float *)take(N * S * cap * 4);
+    w.sp_mem = (float *)take(N * S * kHW * 4);
+    w.se_mem = (float *)take(N * S * kE * 4);
+    w.bytes = o;
+    return w;
+}
+
+static int conv_gemm(const ConvGemmArgs &a, bool tc, cudaStream_t s) {
+    return tc ? conv_gemm_tc(a, s) : conv_gemm_simt(a, s);
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t n_heads, int32_t steps) {
+    if (n_images <= 0 || n_streams <= 0 || n_heads <= 0 || steps <= 0) return 0;
+    return carve(nullptr, n_images, n_streams, n_heads, steps).bytes;
+}
+
+extern "C" int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
+                              int32_t transpose, float scale, spb_stream stream) {
+    SPB_CHECK_ARG(d_x && d_hi && d_lo, "null device pointer");
+    SPB_CHECK_ARG(n_outer > 0 && C > 0 && HW > 0, "bad sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (transpose) {
+        SPB_CHECK_ARG(n_outer <= 65535, "too many outer slices for one launch");
+        dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n_outer);
+        split_transpose_kernel<<<grid, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, C, HW, scale);
+    } else {
+        const int64_t total = n_outer * C * HW;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale);
+    }
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
+extern "C" int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, const void *d_w_lo,
+                             const int32_t *d_w_row_base, int64_t w_rows, const float *d_bias, float *d_out,
+                             int64_t ldo, int32_t n_images, int32_t cols, int32_t ks, float inv_scale,
+                             int32_t use_tensor_cores, spb_stream stream) {
+    SPB_CHECK_ARG(d_a_hi && d_a_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
+    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
+    ConvGemmArgs a{(const __half *)d_a_hi, (const __half *)d_a_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
+                   d_w_row_base, w_rows, d_bias, d_out, ldo, n_images, cols, ks, inv_scale};
+    return conv_gemm(a, use_tensor_cores != 0, (cudaStream_t)stream);
+}
+
+#define SPB_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != SPB_OK) return rc__; \
+    } while (0)
+
+extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream) {
+    SPB_CHECK_ARG(w && io, "null struct pointer");
+    SPB_CHECK_ARG(io->n_images > 0 && io->steps > 0 && io->steps <= 31, "bad sizes");
+    SPB_CHECK_ARG(w->n_streams >= 1 && w->n_streams <= 2 && w->n_heads == w->n_streams, "streams/heads must be 1/1 or 2/2");
+    SPB_CHECK_ARG(io->d_vf && io->d_workspace && io->d_probs && io->d_mu && io->d_sigma2 && io->d_action_map,
+                  "null device pointer");
+    SPB_CHECK_ARG(((uintptr_t)io->d_workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+    const int64_t N = io->n_images;
+    const int S = w->n_streams, HD = w->n_heads, T = io->steps, cap = T + 1;
+    const Workspace ws = carve(io->d_workspace, N, S, HD, T);
+    if (ws.bytes > io->workspace_bytes) {
+        set_error("spb_decode: workspace too small (%lld < %lld bytes)", (long long)io->workspace_bytes, (long long)ws.bytes);
+        return SPB_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tc = io->use_tensor_cores != 0;
+    const int64_t NP = N * kHW;
+
+    // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
+    SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, stream));
+    vfmean_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(io->d_vf, ws.vfmean, N);
+    SPB_LAUNCH_CHECK();
+    {
+        ConvGemmArgs a{ws.vf_hi, ws.vf_lo, (const __half *)w->wx_hi, (const __half *)w->wx_lo, nullptr, kGateCols,
+                       w->bias_gate, ws.xg, kGateCols, (int)N, kGateCols, 3, w->inv_scale_x};
+        SPB_TRY(conv_gemm(a, tc, s));
+    }
+    SPB_CUDA(cudaMemsetAsync(ws.h_hi, 0, NP * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.h_lo, 0, NP * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.c, 0, NP * kE * 4, s));
+
+    auto feedback_tail = [&](int list_index) -> int {
+        // spatial_embed / semantic_embed (:197-198, :336, :339) then the two memory attentions
+        SPB_TRY(sgemm_nt(ws.sp_feat, kHW, w->w_spatial_embed, kHW, w->b_spatial_embed, ws.sp_new, kHW, (int)(N * S),
+                         kHW, kHW, s));
+        SPB_TRY(sgemm_nt(ws.se_feat, kE, w->w_semantic_embed, kE, w->b_semantic_embed, ws.se_new, kE, (int)(N * S), kE,
+                         kE, s));
+        attention_update_kernel<<<(unsigned)(N * S), 256, 0, s>>>(ws.sp_new, ws.se_new, w->w_eff_spatial, w->u_semantic,
+                                                                  ws.sp_list, ws.se_list, ws.sp_score, ws.se_score,
+                                                                  ws.sp_mem, ws.se_mem, list_index, cap);
+        SPB_LAUNCH_CHECK();
+        return SPB_OK;
+    };
+
+    // ---- memories seeded from the attention map (zeros for OSIE) (:333-343)
+    init_spatial_feat_kernel<<<(unsigned)((N * S * kHW + 255) / 256), 256, 0, s>>>(io->d_att, ws.vfmean, ws.sp_feat, S, N);
+    SPB_LAUNCH_CHECK();
+    semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(io->d_vf, io->d_att, kHW, 0, S,
+                                                                              ws.se_feat, N);
+    SPB_LAUNCH_CHECK();
+    SPB_TRY(feedback_tail(0));
+
+    for (int t = 0; t < T; ++t) {
+        // rank-1 gate projections V[n,s,g,co,tap] = sum_ci W[s,g,co,tap,ci] * semantic_mem[n,s,ci]
+        for (int st = 0; st < S; ++st)
+            SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
+                             ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
+        // 3x3 gate convolutions of h
+        {
+            ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr, kGateCols,
+                           nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
+            SPB_TRY(conv_gemm(a, tc, s));
+        }
+        lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi,
+                                                                         ws.h_lo, N, S);
+        SPB_LAUNCH_CHECK();
+        // 5x5 layer(s) on the new h
+        {
+            ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wp_hi, (const __half *)w->wp_lo, io->d_w_row_base,
+                           (int64_t)w->n_weight_sets * kE, w->bias_p, ws.feat, (int64_t)HD * kE, (int)N, HD * kE, 5,
+                           w->inv_scale_p};
+            SPB_TRY(conv_gemm(a, tc, s));
+        }
+        head_reduce_kernel<<<(unsigned)((N * HD * kHW * 32 + 255) / 256), 256, 0, s>>>(ws.feat, HD, w->w2, w->w3, w->wd1,
+                                                                                      ws.y2, ws.y3, ws.dc, N);
+        SPB_LAUNCH_CHECK();
+        head_finish_kernel<<<(unsigned)(N * HD), 256, 0, s>>>(ws.y2, ws.y3, ws.dc, w->wd2, *w, ws.vfmean, ws.sp_feat,
+                                                              io->d_probs, io->d_mu, io->d_sigma2, io->d_action_map, HD,
+                                                              N, t, T);
+        SPB_LAUNCH_CHECK();
+        if (t + 1 < T) {
+            // semantic feedback from this step's action map(s): map of (head hd, image n) lives at
+            // d_action_map[((hd*N + n)*T + t)*1200]
+            semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(
+                io->d_vf, io->d_action_map + (int64_t)t * kHW, (int64_t)T * kHW, N * (int64_t)T * kHW, S, ws.se_feat, N);
+            SPB_LAUNCH_CHECK();
+            SPB_TRY(feedback_tail(t + 1));
+        }
+    }
+    return SPB_OK;
+}

@@ -1,0 +1,33 @@
+// Internal declarations shared by the decoder sources (decode.cu, conv_tc.cu).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace spb {
+
+constexpr int kE = 512;          // embedding channels
+constexpr int kH = 30, kW = 40, kHW = 1200;
+constexpr int kGateCols = 4 * kE;   // i, f, o, g
+constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
+
+// One implicit-GEMM convolution:  out[(n*1200+p)*ldo + col] = inv_scale * conv(a, w)[p, col] (+ bias[col])
+//   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
+//   w  = w_hi + w_lo / 2^11   fp16 [rows, ks*ks*512], K index = (ky*ks+kx)*512 + ci, pre-multiplied by 1/inv_scale
+//   row of w used for output column `col` of image n:  w_row_base[n] + col   (w_row_base NULL -> 0)
+struct ConvGemmArgs {
+    const __half *a_hi, *a_lo;
+    const __half *w_hi, *w_lo;
+    const int32_t *w_row_base;
+    int64_t w_rows;               // total rows of w (for the tensor map)
+    const float *bias;            // [cols] indexed like w rows (after w_row_base), or NULL
+    float *out;
+    int64_t ldo;
+    int n_images, cols, ks;
+    float inv_scale;
+};
+
+int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s);
+int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s);     // tcgen05 / TMEM / TMA (conv_tc.cu)
+
+}  // namespace spb

@@ -1,0 +1,293 @@
+"""Drop-in for the reference's model entry points on the GPU.
+
+``baseline`` keeps the constructor / ``forward`` signatures and the state_dict key
+names of the three reference models
+
+    OSIE/models/baseline_attention.py            baseline(images)
+    AiR/models/baseline_attention.py             baseline(images, attention_maps[, performances])
+    COCO_Search18/models/baseline_attention_multihead.py  baseline(images, attention_maps, tasks)
+
+so a reference checkpoint loads unchanged (utils/checkpointing.py:79-110).  The
+once-per-image encoder (dilated ResNet-50 + sal_conv, :191-194, :327-328) stays in
+PyTorch; everything from ``state = init_hidden`` on (:333-396) runs in the CUDA
+decoder (csrc/decode.cu + csrc/conv_tc.cu) through ``spb_decode``.  ``decode()``
+takes ``visual_feature`` directly (what bench.py and the tests feed).
+
+Inference only: the reference's SCST loop back-propagates through this forward
+(train.py:216, 256); that differentiable path stays with PyTorch and is out of
+scope here -- calling with autograd enabled raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from ..weights import COCO_OBJECTS
+
+E, HW, A = 512, 1200, 1201
+GATES_H = ("input_h", "forget_h", "output_h", "memory_h")
+GATES_X = ("input_x", "forget_x", "output_x", "memory_x")
+
+
+DecoderWeights, DecoderIO = _lib.DecoderWeights, _lib.DecoderIO
+
+
+def split_pair(w: torch.Tensor):
+    """fp32 tensor -> (hi, lo) fp16 with w * scale = hi + lo / 2^11, scale a power of two
+    that puts max|w| in [32, 64).  Returns (hi, lo, 1/scale)."""
+    mx = float(w.abs().max())
+    scale = 2.0 ** (5 - math.floor(math.log2(mx))) if mx > 0 else 1.0
+    ws = w.double() * scale
+    hi = ws.to(torch.float16)
+    lo = ((ws - hi.double()) * 2048.0).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), 1.0 / scale
+
+
+def _conv_to_gemm(w):
+    """[co, ci, kh, kw] -> [co, (ky*kw + kx)*ci_count + ci]"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _interleave_gates(mats):
+    """4 x [512, K] (i, f, o, g) -> [2048, K] rows ordered [channel block of 64][gate][64]."""
+    g = torch.stack(mats, 0)                                  # [4, 512, K]
+    return g.view(4, 8, 64, -1).permute(1, 0, 2, 3).reshape(2048, -1).contiguous()
+
+
+def prepare_weights(sd, task: str, device):
+    """Reference state_dict (fp32, any device) -> prepared device tensors + the C struct."""
+    f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    streams = ["_pos", "_neg"] if task == "AiR" else [""]
+    if task == "AiR":
+        sets = ["performance_sal_layer.True", "performance_sal_layer.False"]      # head 0 = good, 1 = poor
+    elif task == "COCO_Search18":
+        sets = ["object_sal_layer.%s" % o for o in COCO_OBJECTS]
+    else:
+        sets = ["performance_sal_layer"]
+    t = {}
+    wx = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_X])
+    wh = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_H])
+    wp = torch.cat([_conv_to_gemm(f(s + ".weight")) for s in sets], 0).contiguous()
+    t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
+    t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
+    t["wp_hi"], t["wp_lo"], isp = split_pair(wp)
+    biases = []
+    for gi, (gx, gh) in enumerate(zip(GATES_X, GATES_H)):
+        b = f("lstm.%s.bias" % gx) + f("lstm.%s.bias" % gh)
+        if gi < 3:
+            for s in streams:
+                b = b + f("lstm.%s%s.bias" % (gx[:-2], s))
+        biases.append(b.view(512, 1))
+    t["bias_gate"] = _interleave_gates(biases).view(-1).contiguous()
+    t["bias_p"] = torch.cat([f(s + ".bias") for s in sets], 0).contiguous()
+    wm = [f("lstm.%s%s.weight" % (g, s)).permute(0, 2, 3, 1).reshape(512, 9, 512)
+          for s in streams for g in ("input", "forget", "output")]
+    t["wm"] = torch.stack(wm, 0).reshape(-1, 512).contiguous()
+    t["w2"] = f("object_head.sal_layer_2.weight").reshape(512).contiguous()
+    t["w3"] = f("object_head.sal_layer_3.weight").reshape(512).contiguous()
+    t["wd1"] = f("object_head.drt_layer_1.weight")[0].permute(1, 2, 0).reshape(49, 512).contiguous()
+    t["wd2"] = f("object_head.drt_layer_2.weight").reshape(2, 48).contiguous()
+    t["w_spatial_embed"] = f("spatial_embed.weight").contiguous()
+    t["b_spatial_embed"] = f("spatial_embed.bias").contiguous()
+    t["w_semantic_embed"] = f("semantic_embed.weight").contiguous()
+    t["b_semantic_embed"] = f("semantic_embed.bias").contiguous()
+    # spatial_att: score_j = <spatial_attention, conv3x3(spatial_lists, list_j)> + const
+    #            = <w_eff, list_j> + const  (adjoint of the 3x3 correlation applied to spatial_attention)
+    watt = f("spatial_att.spatial_attention.weight").double().view(1, 1, 30, 40)
+    kl = f("spatial_att.spatial_lists.weight").double().view(1, 1, 3, 3)
+    t["w_eff_spatial"] = F.conv_transpose2d(watt, kl, padding=1).reshape(1200).float().contiguous()
+    # semantic_att: score_j = semantic_attention . (semantic_lists list_j) + const = <u, list_j> + const
+    t["u_semantic"] = (f("semantic_att.semantic_attention.weight").double().view(1, 512)
+                       @ f("semantic_att.semantic_lists.weight").double()).reshape(512).float().contiguous()
+    sc = lambda k: float(sd[k].detach().reshape(-1)[0])
+    w = DecoderWeights()
+    for k, v in t.items():
+        setattr(w, k, v.data_ptr())
+    w.b2, w.b3, w.bd1 = sc("object_head.sal_layer_2.bias"), sc("object_head.sal_layer_3.bias"), sc(
+        "object_head.drt_layer_1.bias")
+    bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
+    w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
+    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p = isx, ish, isp
+    w.n_streams = w.n_heads = len(streams)
+    w.n_weight_sets = len(sets)
+    return t, w
+
+
+class CudaDecoder:
+    """Owns the prepared weights and the workspace of one device; runs spb_decode in waves."""
+
+    def __init__(self, state_dict, task="OSIE", steps=16, device="cuda", wave=256, use_tensor_cores=True):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.task, self.steps, self.wave = task, int(steps), int(wave)
+        self.device = torch.device(device)
+        self.use_tensor_cores = bool(use_tensor_cores)
+        self.tensors, self.w = prepare_weights(state_dict, task, self.device)
+        self.heads = int(self.w.n_heads)
+        self._ws, self._ws_n = None, 0
+
+    def _workspace(self, n):
+        if self._ws is None or self._ws_n < n:
+            nbytes = self.lib.spb_decoder_workspace_bytes(n, self.w.n_streams, self.w.n_heads, self.steps)
+            self._ws = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=self.device)
+            self._ws_n = n
+        off = (-self._ws.data_ptr()) % 1024
+        return self._ws.data_ptr() + off, self._ws.numel() - off
+
+    def decode(self, visual_feature, attention_maps=None, tasks=None):
+        """visual_feature [N,512,30,40] f32 (device).  Returns probs [HD,N,T,1201], mu, sigma2 [HD,N,T],
+        action_map [HD,N,T,30,40] (HD = 2 for AiR: good, poor)."""
+        vf = visual_feature.detach().to(self.device, torch.float32).contiguous()
+        N, T, HD = vf.shape[0], self.steps, self.heads
+        assert vf.shape[1:] == (E, 30, 40), "visual_feature must be [N,512,30,40]"
+        dev = self.device
+        probs = torch.empty((HD, N, T, A), dtype=torch.float32, device=dev)
+        mu = torch.empty((HD, N, T), dtype=torch.float32, device=dev)
+        s2 = torch.empty((HD, N, T), dtype=torch.float32, device=dev)
+        amap = torch.empty((HD, N, T, HW), dtype=torch.float32, device=dev)
+        att = None
+        if attention_maps is not None and self.task != "OSIE":
+            att = attention_maps.detach().to(dev, torch.float32).reshape(N, HW).contiguous()
+        rows = None
+        if self.task == "COCO_Search18":
+            assert tasks is not None, "COCO-Search18 decoding needs the task ids"
+            rows = (torch.as_tensor(tasks).to(dev).to(torch.int32) * E).contiguous()
+        for n0 in range(0, N, self.wave):
+            n1 = min(N, n0 + self.wave)
+            n = n1 - n0
+            ws_ptr, ws_bytes = self._workspace(n if N <= self.wave else self.wave)
+            # per-wave outputs are strided views of [HD, N, ...]; the kernels want dense [HD, n, ...]
+            dense = (n == N)
+            p_w = probs if dense else torch.empty((HD, n, T, A), dtype=torch.float32, device=dev)
+            m_w = mu if dense else torch.empty((HD, n, T), dtype=torch.float32, device=dev)
+            s_w = s2 if dense else torch.empty((HD, n, T), dtype=torch.float32, device=dev)
+            a_w = amap if dense else torch.empty((HD, n, T, HW), dtype=torch.float32, device=dev)
+            io = DecoderIO(n, T, 1 if self.use_tensor_cores else 0, 0, vf[n0:n1].data_ptr(),
+                           att[n0:n1].data_ptr() if att is not None else None,
+                           rows[n0:n1].data_ptr() if rows is not None else None, ws_ptr, ws_bytes, p_w.data_ptr(),
+                           m_w.data_ptr(), s_w.data_ptr(), a_w.data_ptr())
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.spb_decode(C.byref(self.w), C.byref(io), _lib.current_stream()), "spb_decode")
+            if not dense:
+                probs[:, n0:n1], mu[:, n0:n1], s2[:, n0:n1], amap[:, n0:n1] = p_w, m_w, s_w, a_w
+        return probs, mu, s2, amap.view(HD, N, T, 30, 40)
+
+
+def _result_dict(task, probs, mu, s2, amap):
+    if task == "AiR":
+        out = {}
+        for i, pre in enumerate(("good_", "poor_")):
+            out[pre + "all_actions_prob"], out[pre + "log_normal_mu"] = probs[i], mu[i]
+            out[pre + "log_normal_sigma2"], out[pre + "action_map"] = s2[i], amap[i]
+        return out
+    return {"all_actions_prob": probs[0], "log_normal_mu": mu[0], "log_normal_sigma2": s2[0], "action_map": amap[0]}
+
+
+class _ConvLSTMParams(nn.Module):
+    def __init__(self, task):
+        super().__init__()
+        names = list(GATES_X) + list(GATES_H)
+        names += ["input_pos", "forget_pos", "output_pos", "input_neg", "forget_neg", "output_neg"] \
+            if task == "AiR" else ["input", "forget", "output"]
+        for n in names:
+            setattr(self, n, nn.Conv2d(E, E, kernel_size=3, padding=1, stride=1, bias=True))
+
+
+class _SemanticAtt(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.semantic_lists = nn.Linear(E, E, bias=True)
+        self.semantic_cur = nn.Linear(E, E, bias=True)
+        self.semantic_attention = nn.Linear(E, 1, bias=True)
+
+
+class _SpatialAtt(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.spatial_lists = nn.Conv2d(1, 1, kernel_size=3, padding=1, stride=1, bias=True)
+        self.spatial_cur = nn.Conv2d(1, 1, kernel_size=3, padding=1, stride=1, bias=True)
+        self.spatial_attention = nn.Conv2d(1, 1, kernel_size=(30, 40), padding=0, stride=1, bias=True)
+
+
+class _PredictHead(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.sal_layer_2 = nn.Conv2d(512, 1, kernel_size=1, padding=0, stride=1, bias=True)
+        self.sal_layer_3 = nn.Conv2d(512, 1, kernel_size=1, padding=0, stride=1, bias=True)
+        self.drt_layer_1 = nn.Conv2d(512, 1, kernel_size=7, padding=2, stride=5, bias=True)
+        self.drt_layer_2 = nn.Conv2d(1, 2, kernel_size=(6, 8), padding=0, stride=1, bias=True)
+
+
+class baseline(nn.Module):
+    """Same parameters (names, shapes) as the reference ``baseline``; ``task`` selects which of the
+    three reference variants is mirrored.  The encoder is attached lazily by ``attach_encoder``."""
+
+    def __init__(self, embed_size=512, convLSTM_length=16, min_length=1, ratio=4, map_width=40, map_height=30,
+                 projected_label_length=18, task="OSIE", wave=256, use_tensor_cores=True):
+        super().__init__()
+        assert embed_size == 512 and map_width == 40 and map_height == 30, "the reference hard-codes 512 x 30 x 40"
+        self.task = task
+        self.embed_size, self.convLSTM_length, self.min_length = embed_size, convLSTM_length, min_length
+        self.map_width, self.map_height = map_width, map_height
+        self.wave, self.use_tensor_cores = wave, use_tensor_cores
+        self.lstm = _ConvLSTMParams(task)
+        self.semantic_embed = nn.Linear(512, embed_size)
+        self.spatial_embed = nn.Linear(1200, 1200, bias=True)
+        self.semantic_att = _SemanticAtt()
+        self.spatial_att = _SpatialAtt()
+        conv5 = lambda: nn.Conv2d(512, 512, kernel_size=5, padding=2, stride=1, bias=True)
+        if task == "AiR":
+            self.performance_sal_layer = nn.ModuleDict({"False": conv5(), "True": conv5()})
+        elif task == "COCO_Search18":
+            self.object_sal_layer = nn.ModuleDict({o: conv5() for o in COCO_OBJECTS})
+        else:
+            self.performance_sal_layer = conv5()
+        self.object_head = _PredictHead()
+        self.resnet = None          # encoder: PyTorch, out of scope of the CUDA path
+        self.sal_conv = None
+        self._decoder = None
+        self.eval()
+
+    def load_state_dict(self, state_dict, strict=False, **kw):
+        self._decoder = None
+        own = {k: v for k, v in state_dict.items() if not k.startswith(("resnet.", "sal_conv."))} \
+            if self.resnet is None else state_dict
+        return super().load_state_dict(own, strict=strict, **kw)
+
+    def decoder(self):
+        if self._decoder is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise _lib.SpbError("scanpaths_b200 has no CPU path: move the model to a CUDA device")
+            sd = {k: v for k, v in self.state_dict().items() if not k.startswith(("resnet.", "sal_conv."))}
+            self._decoder = CudaDecoder(sd, self.task, self.convLSTM_length, dev, self.wave, self.use_tensor_cores)
+        return self._decoder
+
+    def decode(self, visual_feature, attention_maps=None, tasks=None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("training_process stays in PyTorch (out of scope); call under eval()")
+        return _result_dict(self.task, *self.decoder().decode(visual_feature, attention_maps, tasks))
+
+    def forward(self, images, attention_maps=None, tasks=None):
+        if self.training:
+            raise NotImplementedError("training_process (with gradients) is out of scope of the CUDA path")
+        if images.shape[1] == E:                       # already visual_feature [N,512,30,40]
+            vf = images
+        else:
+            if self.resnet is None:
+                raise _lib.SpbError("no encoder attached: pass visual_feature [N,512,30,40] or attach_encoder()")
+            vf = F.relu(self.sal_conv(self.resnet(images)))
+        return self.decode(vf, attention_maps, tasks)
+
+
+def smoke_decode(n, device):
+    """Tiny decode used by __graft_entry__.smoke(): random-init OSIE weights, synthetic features."""
+    from ..weights import random_state_dict, synthetic_features
+    dec = CudaDecoder(random_state_dict("OSIE", 0), "OSIE", 16, device, wave=n)
+    probs, mu, s2, _ = dec.decode(synthetic_features(n, 0).to(device))
+    return probs[0], mu[0], s2[0]

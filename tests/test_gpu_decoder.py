@@ -1,0 +1,143 @@
+"""Parity of the CUDA decoder (csrc/decode.cu, csrc/conv_tc.cu through spb_decode /
+spb_conv_gemm) with the float64 outputs of the reference modules recorded in
+tests/golden/decoder_*.npz.  Gate (north_star): per-step probabilities, mu and
+sigma2 within 1e-5 relative."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from scanpaths_b200 import build, _lib
+    build.build_library()
+    return _lib.load()
+
+
+def _conv_case(lib, ks, n_images, cols, use_tc, per_image_sets=0, seed=0):
+    from scanpaths_b200 import _lib
+    from scanpaths_b200.models.baseline_attention import split_pair
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    a = torch.randn(n_images, 30, 40, 512, generator=g, device=dev) * 0.7
+    a[a.abs() < 0.05] = 0.0                                    # exact zeros and tiny values too
+    rows = cols * max(per_image_sets, 1)
+    w = torch.randn(rows, ks, ks, 512, generator=g, device=dev) * 0.02
+    bias = torch.randn(rows, generator=g, device=dev)
+    a_hi = torch.empty_like(a, dtype=torch.float16); a_lo = torch.empty_like(a_hi)
+    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0,
+                                  _lib.current_stream()), "split")
+    # the device split equals the host one
+    hi_ref = a.double().to(torch.float16)
+    assert torch.equal(a_hi, hi_ref)
+    assert torch.equal(a_lo, ((a.double() - hi_ref.double()) * 2048).to(torch.float16))
+    w_hi, w_lo, inv = split_pair(w.reshape(rows, -1))
+    base = None
+    if per_image_sets:
+        base = (torch.arange(n_images, device=dev, dtype=torch.int32) * 7 % per_image_sets * cols).to(torch.int32)
+    out = torch.full((n_images * 1200, cols + 4), -7.0, device=dev)
+    _lib.check(lib.spb_conv_gemm(_lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(base), rows,
+                                 _lib.ptr(bias), _lib.ptr(out), cols + 4, n_images, cols, ks, inv, int(use_tc),
+                                 _lib.current_stream()), "spb_conv_gemm")
+    torch.cuda.synchronize()
+    ref = []
+    for n in range(n_images):
+        r0 = int(base[n]) if base is not None else 0
+        wn = w[r0:r0 + cols].permute(0, 3, 1, 2).double()
+        y = F.conv2d(a[n:n + 1].permute(0, 3, 1, 2).double(), wn, bias[r0:r0 + cols].double(), padding=ks // 2)
+        ref.append(y[0].permute(1, 2, 0).reshape(1200, cols))
+    ref = torch.cat(ref, 0)
+    assert torch.all(out[:, cols:] == -7.0), "wrote outside its columns"
+    err = (out[:, :cols].double() - ref).abs().max().item()
+    return err, ref.abs().max().item()
+
+
+@pytest.mark.parametrize("ks,cols", [(3, 256), (5, 512)])
+def test_conv_gemm_simt_vs_torch_fp64(lib, ks, cols):
+    err, mag = _conv_case(lib, ks, 2, cols, use_tc=False)
+    assert err < 2e-6 * mag, (err, mag)
+
+
+@pytest.mark.parametrize("ks,cols,sets", [(3, 256, 0), (3, 2048, 0), (5, 512, 0), (5, 512, 3)])
+def test_conv_gemm_tensor_core_vs_torch_fp64(lib, ks, cols, sets):
+    err, mag = _conv_case(lib, ks, 3, cols, use_tc=True, per_image_sets=sets)
+    assert err < 2e-6 * mag, (err, mag)
+
+
+def _decode_case(name, use_tc, golden_dir, steps=None):
+    from golden.make_decoder_goldens import CASES, COCO_TASKS
+    from scanpaths_b200.models.baseline_attention import CudaDecoder
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    task, n, T, wseed, fseed, bstd = CASES[name]
+    T = steps or T
+    g = np.load(os.path.join(golden_dir, "decoder_%s.npz" % name))
+    sd = random_state_dict(task, wseed, calibrated=True, bias_std=bstd)
+    dev = torch.device("cuda")
+    dec = CudaDecoder(sd, task, T, dev, wave=n, use_tensor_cores=use_tc)
+    if task == "OSIE":
+        vf, att, tasks = synthetic_features(n, fseed), None, None
+    else:
+        vf, att = synthetic_features(n, fseed, attention=True)
+        tasks = COCO_TASKS[:n] if task == "COCO_Search18" else None
+    probs, mu, s2, amap = dec.decode(vf.to(dev), None if att is None else att.to(dev), tasks)
+    torch.cuda.synchronize()
+    prefixes = ["good_", "poor_"] if task == "AiR" else [""]
+    worst = {}
+    for hi, pre in enumerate(prefixes):
+        for key, got in (("all_actions_prob", probs[hi]), ("log_normal_mu", mu[hi]), ("log_normal_sigma2", s2[hi])):
+            ref = g["f64_" + pre + key][:, :T]
+            rel = np.abs(got.cpu().numpy().astype(np.float64) - ref) / np.abs(ref)
+            worst[pre + key] = float(rel.max())
+        ref = g["f64_" + pre + "action_map"][:, :T]
+        worst[pre + "action_map(abs)"] = float(np.abs(amap[hi].cpu().numpy() - ref).max())
+        # the float32 reference's own distance from float64, for context
+        r32 = g["f32_" + pre + "all_actions_prob"][:, :T].astype(np.float64)
+        worst[pre + "ref_f32_prob"] = float((np.abs(r32 - g["f64_" + pre + "all_actions_prob"][:, :T]) /
+                                             g["f64_" + pre + "all_actions_prob"][:, :T]).max())
+    return worst
+
+
+@pytest.mark.parametrize("name", ["coco", "air", "osie"])
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
+    worst = _decode_case(name, use_tc, golden_dir)
+    print(name, "tc" if use_tc else "simt", worst)
+    for k, v in worst.items():
+        if k.endswith("ref_f32_prob"):
+            continue
+        assert v < RTOL, (k, v, worst)
+
+
+def test_decode_waves_and_module_api(lib, golden_dir):
+    """baseline module: reference state_dict keys load, waves smaller than the batch give the same result."""
+    from golden.make_decoder_goldens import CASES
+    from scanpaths_b200.models.baseline_attention import baseline
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    task, n, T, wseed, fseed, bstd = CASES["osie"]
+    sd = random_state_dict(task, wseed, calibrated=True, bias_std=bstd)
+    m = baseline(convLSTM_length=4, task="OSIE", wave=1).cuda()
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    vf = synthetic_features(3, fseed).cuda()
+    with torch.no_grad():
+        a = m(vf)
+    m2 = baseline(convLSTM_length=4, task="OSIE", wave=8).cuda()
+    m2.load_state_dict(sd)
+    with torch.no_grad():
+        b = m2(vf)
+    assert set(a) == {"all_actions_prob", "log_normal_mu", "log_normal_sigma2", "action_map"}
+    assert a["all_actions_prob"].shape == (3, 4, 1201) and a["action_map"].shape == (3, 4, 30, 40)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    g = np.load(os.path.join(golden_dir, "decoder_osie.npz"))
+    ref = g["f64_all_actions_prob"][:2, :4]
+    rel = np.abs(a["all_actions_prob"][:2].cpu().numpy() - ref) / ref
+    assert rel.max() < RTOL
