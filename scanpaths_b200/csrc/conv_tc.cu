@@ -16,8 +16,15 @@
 //     x = hi + lo / 2^11 (11 + 11 significand bits).  Three MMAs per k-step:
 //     hi*hi -> accumulator 0, hi*lo + lo*hi -> accumulator 1 (scaled by 2^11), combined in
 //     the epilogue.  The dropped lo*lo term is 2^-22 relative.  TMEM: 2 x 256 fp32 columns.
+//   * the tensor core adds into its fp32 accumulator with truncation (measured on B200:
+//     -1.6e-8 relative per accumulation step, i.e. -4.5e-6 after K = 4608 and -1.2e-5 after
+//     K = 12800 -- outside the 1e-5 parity gate).  So accumulator 0 only ever holds ONE
+//     filter tap (32 k-steps): after each tap the 8 epilogue warps drain it from TMEM and add
+//     it to running totals in registers (round-to-nearest), while the MMA thread already
+//     issues the correction MMAs of the next k-block (accumulator 1 is never drained
+//     mid-loop: its values weigh 2^-11).
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator,
-//     warps 2-5 epilogue (tcgen05.ld 32 lanes x 16 columns -> scale/bias -> 64 B stores).
+//     warps 2-9 drain/epilogue (each thread: 1 TMEM lane x 128 columns of running totals).
 //   * operands staged by TMA with 128-byte swizzle, K-major; kStages-deep mbarrier ring.
 #include <cuda.h>
 
@@ -34,7 +41,8 @@ constexpr int kBBytes = kBlockN * kBlockK * 2;            // 32 KB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;    // 96 KB
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kChunkKB = kE / kBlockK;                   // k-blocks per drained chunk: one filter tap
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -116,8 +124,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t bar0 = base + kStages * kStageBytes;
     auto full_bar = [&](int s) { return bar0 + 8 * s; };
     auto empty_bar = [&](int s) { return bar0 + 8 * (kStages + s); };
-    const uint32_t tmem_full_bar = bar0 + 8 * (2 * kStages);
-    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 1);
+    const uint32_t main_full_bar = bar0 + 8 * (2 * kStages);        // MMA -> drain warps: one tap accumulated
+    const uint32_t main_empty_bar = bar0 + 8 * (2 * kStages + 1);   // drain warps -> MMA: accumulator 0 read out
+    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y, img = blockIdx.z;
@@ -130,7 +139,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        mbar_init(main_full_bar, 1);
+        mbar_init(main_empty_bar, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -169,43 +179,77 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const uint32_t d_main = tmem_base, d_corr = tmem_base + kBlockN;
             for (int kb = 0; kb < kNumKB; ++kb) {
                 const int s = kb % kStages;
+                const int chunk = kb / kChunkKB, kc = kb % kChunkKB;
                 mbar_wait(full_bar(s), (kb / kStages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = base + s * kStageBytes;
                 const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
                 const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
+                // correction products first: they do not touch accumulator 0, which the drain
+                // warps may still be reading at a chunk boundary
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                    umma_f16(d_main, a_hi + adv, b_hi + adv, acc);
-                    umma_f16(d_corr, a_hi + adv, b_lo + adv, acc);
+                    umma_f16(d_corr, a_hi + adv, b_lo + adv, (kb > 0 || k > 0) ? 1u : 0u);
                     umma_f16(d_corr, a_lo + adv, b_hi + adv, 1u);
                 }
+                if (kc == 0 && chunk > 0) {
+                    mbar_wait(main_empty_bar, (chunk - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    umma_f16(d_main, a_hi + adv, b_hi + adv, (kc > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(empty_bar(s));            // frees this smem stage once the MMAs have read it
+                if (kc == kChunkKB - 1) umma_commit(main_full_bar);   // this tap's partial sum is complete
             }
-            umma_commit(tmem_full_bar);               // accumulators complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== drain + epilogue warps: TMEM -> registers (running totals) -> global =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // column half: warps 2-5 -> 0, warps 6-9 -> 1
         const int r = q * 32 + lane;
         const bool valid = r < kValidM;
-        const int64_t orow = ((int64_t)img * kHW + m_tile * kValidM + r) * a.ldo + n_tile * kBlockN;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c = 0; c < kBlockN; c += 16) {
-            uint32_t vm[16], vc[16];
-            tmem_ld16(lane_addr + c, vm);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * (kBlockN / 2);
+        float tot[kBlockN / 2];
+#pragma unroll
+        for (int j = 0; j < kBlockN / 2; ++j) tot[j] = 0.0f;
+        constexpr int kNumChunks = kNumKB / kChunkKB;
+        for (int chunk = 0; chunk < kNumChunks; ++chunk) {
+            mbar_wait(main_full_bar, chunk & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < kBlockN / 2; c += 32) {
+                uint32_t v0[16], v1[16];
+                tmem_ld16(lane_addr + c, v0);
+                tmem_ld16(lane_addr + c + 16, v1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    tot[c + j] += __uint_as_float(v0[j]);
+                    tot[c + 16 + j] += __uint_as_float(v1[j]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(main_empty_bar) : "memory");
+        }
+        // the last main_full commit also covers every correction MMA issued before it
+        const int64_t orow = ((int64_t)img * kHW + m_tile * kValidM + r) * a.ldo + n_tile * kBlockN + half * (kBlockN / 2);
+        const int bias0 = row_base + half * (kBlockN / 2);
+#pragma unroll
+        for (int c = 0; c < kBlockN / 2; c += 16) {
+            uint32_t vc[16];
             tmem_ld16(lane_addr + kBlockN + c, vc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (valid) {
                 float o[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float v = (__uint_as_float(vm[j]) + __uint_as_float(vc[j]) * (1.0f / kLoScale)) * a.inv_scale;
-                    if (a.bias) v += a.bias[row_base + c + j];
+                    float v = (tot[c + j] + __uint_as_float(vc[j]) * (1.0f / kLoScale)) * a.inv_scale;
+                    if (a.bias) v += a.bias[bias0 + c + j];
                     o[j] = v;
                 }
                 float4 *dst = reinterpret_cast<float4 *>(a.out + orow + c);
