@@ -46,6 +46,9 @@ P, I32, I64, U64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
 SYMBOLS = {
     "spb_version": (C.c_int, []),
     "spb_last_error": (C.c_char_p, []),
+    "spb_kernel_launches": (C.c_int64, []),
+    "spb_profile_enable": (C.c_int, [C.c_int32]),
+    "spb_profile_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "spb_scanmatch_tables": (C.c_int, [C.POINTER(ScanMatchCfg), P, P, P, P, P]),
     "spb_prep_paths": (C.c_int, [P, P, I64, I32, C.POINTER(ScoreCfg), P, P, P, P, P, P]),
     "spb_score_workspace_bytes": (I64, [I64]),

@@ -1,5 +1,8 @@
 // Error plumbing + host-side ScanMatch tables (C ABI, see include/scanpaths_b200.h).
 #include <math.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -16,7 +19,67 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace spb
 
+namespace spb {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct Prof {
+    std::vector<cudaEvent_t> ev;     // 2 per pair
+    std::vector<int> tags;
+    int cap = 0, n = 0;
+    bool open = false;
+};
+static Prof g_prof;
+static std::mutex g_prof_mu;
+
+void prof_begin(int tag, cudaStream_t s) {
+    if (g_prof.cap == 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof.n >= g_prof.cap || g_prof.open) return;
+    g_prof.tags[g_prof.n] = tag;
+    cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+    g_prof.open = true;
+}
+void prof_end(cudaStream_t s) {
+    if (g_prof.cap == 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.open) return;
+    cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s);
+    g_prof.open = false;
+    ++g_prof.n;
+}
+}  // namespace spb
+
 extern "C" int spb_version(void) { return 100; }
+
+extern "C" int64_t spb_kernel_launches(void) { return spb::g_launches.load(); }
+
+extern "C" int spb_profile_enable(int32_t max_pairs) {
+    std::lock_guard<std::mutex> lk(spb::g_prof_mu);
+    for (cudaEvent_t e : spb::g_prof.ev) cudaEventDestroy(e);
+    spb::g_prof.ev.clear(); spb::g_prof.tags.clear();
+    spb::g_prof.cap = 0; spb::g_prof.n = 0; spb::g_prof.open = false;
+    if (max_pairs <= 0) return SPB_OK;
+    spb::g_prof.ev.resize(2 * (size_t)max_pairs);
+    spb::g_prof.tags.resize(max_pairs);
+    for (auto &e : spb::g_prof.ev) SPB_CUDA(cudaEventCreate(&e));
+    spb::g_prof.cap = max_pairs;
+    return SPB_OK;
+}
+
+extern "C" int spb_profile_collect(float *h_ms, int32_t *h_tags, int32_t cap, int32_t *n_out) {
+    SPB_CHECK_ARG(h_ms && h_tags && n_out, "null pointer");
+    std::lock_guard<std::mutex> lk(spb::g_prof_mu);
+    int n = spb::g_prof.n < cap ? spb::g_prof.n : cap;
+    for (int i = 0; i < n; ++i) {
+        SPB_CUDA(cudaEventSynchronize(spb::g_prof.ev[2 * i + 1]));
+        SPB_CUDA(cudaEventElapsedTime(&h_ms[i], spb::g_prof.ev[2 * i], spb::g_prof.ev[2 * i + 1]));
+        h_tags[i] = spb::g_prof.tags[i];
+    }
+    *n_out = n;
+    spb::g_prof.n = 0;
+    return SPB_OK;
+}
 
 extern "C" const char *spb_last_error(void) { return spb::g_err; }
 

@@ -9,6 +9,12 @@
 namespace spb {
 
 void set_error(const char *fmt, ...);
+void count_launch();
+// optional live profiling: CUDA-event pairs around tagged launches (see spb_profile_enable)
+enum ProfTag { kTagConvX = 1, kTagConvH = 2, kTagConvP = 3, kTagCell = 4, kTagHead = 5, kTagFeedback = 6, kTagRank1 = 7,
+               kTagPrep = 8 };
+void prof_begin(int tag, cudaStream_t s);
+void prof_end(cudaStream_t s);
 
 #define SPB_CHECK_ARG(cond, msg)                                   \
     do {                                                           \
@@ -30,6 +36,7 @@ void set_error(const char *fmt, ...);
 #define SPB_LAUNCH_CHECK()                                                                   \
     do {                                                                                     \
         cudaError_t e__ = cudaGetLastError();                                                \
+        spb::count_launch();                                                                 \
         if (e__ != cudaSuccess) {                                                            \
             spb::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
             return SPB_ERR_CUDA;                                                             \

@@ -587,14 +587,18 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     const int64_t NP = N * kHW;
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
+    prof_begin(kTagPrep, s);
     SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, stream));
     vfmean_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(io->d_vf, ws.vfmean, N);
     SPB_LAUNCH_CHECK();
+    prof_end(s);
+    prof_begin(kTagConvX, s);
     {
         ConvGemmArgs a{ws.vf_hi, ws.vf_lo, (const __half *)w->wx_hi, (const __half *)w->wx_lo, nullptr, kGateCols,
                        w->bias_gate, ws.xg, kGateCols, (int)N, kGateCols, 3, w->inv_scale_x};
         SPB_TRY(conv_gemm(a, tc, s));
     }
+    prof_end(s);
     SPB_CUDA(cudaMemsetAsync(ws.h_hi, 0, NP * kE * 2, s));
     SPB_CUDA(cudaMemsetAsync(ws.h_lo, 0, NP * kE * 2, s));
     SPB_CUDA(cudaMemsetAsync(ws.c, 0, NP * kE * 4, s));
@@ -618,29 +622,40 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(io->d_vf, io->d_att, kHW, 0, S,
                                                                               ws.se_feat, N);
     SPB_LAUNCH_CHECK();
+    prof_begin(kTagFeedback, s);
     SPB_TRY(feedback_tail(0));
+    prof_end(s);
 
     for (int t = 0; t < T; ++t) {
+        prof_begin(kTagRank1, s);
         // rank-1 gate projections V[n,s,g,co,tap] = sum_ci W[s,g,co,tap,ci] * semantic_mem[n,s,ci]
         for (int st = 0; st < S; ++st)
             SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
                              ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
+        prof_end(s);
         // 3x3 gate convolutions of h
+        prof_begin(kTagConvH, s);
         {
             ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr, kGateCols,
                            nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
             SPB_TRY(conv_gemm(a, tc, s));
         }
+        prof_end(s);
+        prof_begin(kTagCell, s);
         lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi,
                                                                          ws.h_lo, N, S);
         SPB_LAUNCH_CHECK();
+        prof_end(s);
         // 5x5 layer(s) on the new h
+        prof_begin(kTagConvP, s);
         {
             ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wp_hi, (const __half *)w->wp_lo, io->d_w_row_base,
                            (int64_t)w->n_weight_sets * kE, w->bias_p, ws.feat, (int64_t)HD * kE, (int)N, HD * kE, 5,
                            w->inv_scale_p};
             SPB_TRY(conv_gemm(a, tc, s));
         }
+        prof_end(s);
+        prof_begin(kTagHead, s);
         head_reduce_kernel<<<(unsigned)((N * HD * kHW * 32 + 255) / 256), 256, 0, s>>>(ws.feat, HD, w->w2, w->w3, w->wd1,
                                                                                       ws.y2, ws.y3, ws.dc, N);
         SPB_LAUNCH_CHECK();
@@ -648,13 +663,16 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                                                               io->d_probs, io->d_mu, io->d_sigma2, io->d_action_map, HD,
                                                               N, t, T);
         SPB_LAUNCH_CHECK();
+        prof_end(s);
         if (t + 1 < T) {
+            prof_begin(kTagFeedback, s);
             // semantic feedback from this step's action map(s): map of (head hd, image n) lives at
             // d_action_map[((hd*N + n)*T + t)*1200]
             semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(
                 io->d_vf, io->d_action_map + (int64_t)t * kHW, (int64_t)T * kHW, N * (int64_t)T * kHW, S, ws.se_feat, N);
             SPB_LAUNCH_CHECK();
             SPB_TRY(feedback_tail(t + 1));
+            prof_end(s);
         }
     }
     return SPB_OK;
