@@ -215,6 +215,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     lib = _lib.load()
+    from scanpaths_b200.dist import allgather_tables
     from scanpaths_b200.pipeline import ScanpathPipeline
     from scanpaths_b200.weights import random_state_dict
 
@@ -242,10 +243,7 @@ def main():
             pipe.set_humans(hx_pin, hl_pin)
         out = pipe.run(vf)
         if world > 1:                                     # the one collective of the path: score tables
-            tab = out["table"].contiguous()
-            buf = torch.empty((world,) + tuple(tab.shape), dtype=tab.dtype, device=dev)
-            dist.all_gather_into_tensor(buf, tab)
-            gathered[0] = buf
+            gathered[0] = allgather_tables(out["table"], world * N, image_dim=2)
         return out
 
     for _ in range(args.warmup):
