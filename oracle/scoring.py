@@ -344,3 +344,103 @@ def pairs_eval_scanmatch(gt_fix_vectors, predict_fix_vectors):
         rows = rows[~np.isnan(rows.sum(axis=1))]               # NaN rows (both wd strings empty) dropped
         out.append(rows.sum(axis=0) / len(gts) if rows.shape[0] else np.array([np.nan] * 2))
     return np.array(out)
+
+
+# --------------------------------------------------------------------------
+# AiR: performance-related drivers (AiR/utils/evaluation.py:188-577)
+# --------------------------------------------------------------------------
+def _sm_pair(a, b, sm_wd, sm_wod):
+    wd = sm_wd.match_score(sm_wd.fixationToSequence(a).astype(np.int32), sm_wd.fixationToSequence(b).astype(np.int32))
+    wod = sm_wod.match_score(sm_wod.fixationToSequence(a).astype(np.int32),
+                             sm_wod.fixationToSequence(b).astype(np.int32))
+    return [wod, wd]
+
+
+def _mean_rows(rows, drop_nan=True):
+    rows = np.array(rows, dtype=np.float64).reshape(-1, 2)
+    flag = True
+    if drop_nan and rows.shape[0] != 0:
+        rows = rows[~np.isnan(rows.sum(axis=1))]
+        flag = rows.shape[0] != 0
+    return (rows.sum(axis=0) / rows.shape[0] if rows.shape[0] else np.array([np.nan] * 2)), flag
+
+
+def pairs_eval_scanmatch_performance_related(gt_fix_vectors, predict_fix_vectors, performance, given_performance,
+                                             is_eliminating_nan=True):
+    """:361-420 -> (same [N,2], diff [N,2], accept_flag): subjects whose performance equals
+    `given_performance` vs the others; columns (SM w/o duration, SM with duration)."""
+    sm_wd, sm_wod = eval_scanmatch_objects()
+    same, diff, accept = [], [], True
+    for i, (gts, pred) in enumerate(zip(gt_fix_vectors, predict_fix_vectors)):
+        p = structured_to_array(pred)
+        s_rows, d_rows = [], []
+        for j, g in enumerate(gts):
+            (s_rows if performance[i][j] == given_performance else d_rows).append(
+                _sm_pair(structured_to_array(g), p, sm_wd, sm_wod))
+        m, f1 = _mean_rows(s_rows, is_eliminating_nan)
+        same.append(m)
+        m, f2 = _mean_rows(d_rows, is_eliminating_nan)
+        diff.append(m)
+        accept = accept and f1 and f2
+    return np.array(same), np.array(diff), accept
+
+
+def gtpairs_eval_scanmatch_performance_related(gt_fix_vectors, performance, is_eliminating_nan=True):
+    """:423-577 -> (good-vs-good, poor-vs-poor, good-vs-poor) [N,2] human-human ScanMatch means."""
+    sm_wd, sm_wod = eval_scanmatch_objects()
+    good_m, poor_m, gp_m = [], [], []
+    for gts, perf in zip(gt_fix_vectors, performance):
+        arrs = [structured_to_array(g) for g in gts]
+        good = [a for a, p in zip(arrs, perf) if p == True]     # noqa: E712 (the reference compares with ==)
+        poor = [a for a, p in zip(arrs, perf) if not (p == True)]  # noqa: E712
+        for grp, dst in ((good, good_m), (poor, poor_m)):
+            rows = []
+            if len(grp) > 1:
+                for a in range(len(grp)):
+                    for b in range(a + 1, len(grp)):
+                        rows.append(_sm_pair(grp[a], grp[b], sm_wd, sm_wod))
+            dst.append(_mean_rows(rows, is_eliminating_nan)[0])
+        rows = []
+        if len(good) > 1 and len(poor) > 1:
+            for a in good:
+                for b in poor:
+                    rows.append(_sm_pair(a, b, sm_wd, sm_wod))
+        gp_m.append(_mean_rows(rows, is_eliminating_nan)[0])
+    return np.array(good_m), np.array(poor_m), np.array(gp_m)
+
+
+def evaluation_performance_related(gt_fix_vectors, predict_fix_vectors, all_performances,
+                                   all_allocated_performances, min_len_valid=3):
+    """:188-359 minus MultiMatch.  Rows are stored as float32 there, so means / stds are float32.
+    Returns (mean [3,6], std [3,6], per_image [N,4]) for the categories (all, right_answer,
+    wrong_answer); the six columns are specific_mean[5:11] = (SM WITH duration, SM w/o duration,
+    SED, STDE, SED_best, STDE_best) -- which AiR then labels 'w/o duration' / 'with duration'
+    the other way round (:321-322)."""
+    sm_wd, sm_wod = eval_scanmatch_objects()
+    cats = [[], [], []]
+    per_image = []
+    for i, (gts, pred) in enumerate(zip(gt_fix_vectors, predict_fix_vectors)):
+        p = structured_to_array(pred)
+        rows = [[], [], []]
+        for j, g in enumerate(gts):
+            if not multimatch_valid(len(g), len(pred), min_len_valid):
+                continue
+            wd, wod, sed, stde = score_pair(structured_to_array(g), p, sm_wd, sm_wod)
+            r = [wd, wod, sed, stde]
+            rows[0].append(r)
+            if all_performances[i][j] == True and all_allocated_performances[i] == True:      # noqa: E712
+                rows[1].append(r)
+            elif all_performances[i][j] == False and all_allocated_performances[i] == False:  # noqa: E712
+                rows[2].append(r)
+        for c in range(3):
+            cats[c].append(np.array(rows[c], dtype=np.float32).reshape(-1, 4))
+        own = rows[1] if all_allocated_performances[i] == True else rows[2]                     # noqa: E712
+        per_image.append(list(np.array(own).mean(axis=0)) if own else [0.0] * 4)
+    mean, std = [], []
+    for c in range(3):
+        groups = [g for g in cats[c] if len(g) != 0]
+        allrows = np.concatenate(groups, axis=0)
+        best = np.array([[g[:, 2].min(), g[:, 3].max()] for g in groups], dtype=np.float32)
+        mean.append(np.concatenate([allrows.mean(0), best.mean(0)]))
+        std.append(np.concatenate([allrows.std(0), best.std(0)]))
+    return np.array(mean), np.array(std), np.array(per_image, dtype=np.float64)

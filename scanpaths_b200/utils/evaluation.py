@@ -174,3 +174,121 @@ def pairs_eval_scanmatch(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDurat
         out.append(rows.sum(axis=0) / s if rows.shape[0] else np.array([np.nan] * 2))
         o += s
     return np.array(out)
+
+
+# ---------------------------------------------------------------------------------------
+# AiR: performance-related drivers (AiR/utils/evaluation.py:188-577).  Same kernels, other
+# pair maps / groupings; the grouping itself is O(pairs) host bookkeeping on the score table.
+# ---------------------------------------------------------------------------------------
+def _score_index_pairs(paths_h, paths_s, pair_h, pair_s, device=None):
+    """Scores explicit (human index, simulated index) pairs of two lists of [L,3] arrays (seconds)."""
+    cfg = _eval_cfg(device)
+    if len(pair_h) == 0:
+        return np.zeros((0, 4))
+    hp = S.pack_paths(paths_h, cfg)
+    sp = hp if paths_s is paths_h else S.pack_paths(paths_s, cfg)
+    dev = cfg.device
+    sc = S.score_pairs(hp, sp, torch.tensor(pair_h, dtype=torch.int32, device=dev),
+                       torch.tensor(pair_s, dtype=torch.int32, device=dev), cfg)
+    return sc.cpu().numpy()
+
+
+def _mean2(rows, drop_nan):
+    """rows [n,2] (wod, wd) -> (mean or NaN, group still non-empty after NaN elimination)."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 2)
+    ok = True
+    if drop_nan and rows.shape[0] != 0:
+        rows = rows[~np.isnan(rows.sum(axis=1))]
+        ok = rows.shape[0] != 0
+    return (rows.sum(axis=0) / rows.shape[0] if rows.shape[0] else np.array([np.nan] * 2)), ok
+
+
+def pairs_eval_scanmatch_performance_related(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None,
+                                             ScanMatchwithoutDuration=None, performance=None, given_performance=True,
+                                             is_eliminating_nan=True):
+    """AiR/utils/evaluation.py:361-420 -> (same [N,2], diff [N,2], accept_flag)."""
+    scores, _, _, _, _, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    sc = scores[:, :2].cpu().numpy()[:, ::-1]              # (wod, wd)
+    same, diff, accept, o = [], [], True, 0
+    for i, s in enumerate(sizes):
+        rows = sc[o:o + s]
+        mask = np.array([performance[i][j] == given_performance for j in range(s)], dtype=bool)
+        m, f1 = _mean2(rows[mask], is_eliminating_nan)
+        same.append(m)
+        m, f2 = _mean2(rows[~mask], is_eliminating_nan)
+        diff.append(m)
+        accept = accept and f1 and f2
+        o += s
+    return np.array(same), np.array(diff), accept
+
+
+def gtpairs_eval_scanmatch_performance_related(gt_fix_vectors, ScanMatchwithDuration=None,
+                                               ScanMatchwithoutDuration=None, performance=None,
+                                               is_eliminating_nan=True):
+    """AiR/utils/evaluation.py:423-577 -> (good v good, poor v poor, good v poor) [N,2]: human-human
+    ScanMatch means inside each image, grouped by answer correctness.  One launch for all images."""
+    paths, pair_h, pair_s, spans = [], [], [], []
+    for gts, perf in zip(gt_fix_vectors, performance):
+        b = len(paths)
+        paths.extend(S.structured_to_xyd(g) for g in gts)
+        good = [b + j for j in range(len(gts)) if perf[j] == True]        # noqa: E712
+        poor = [b + j for j in range(len(gts)) if not (perf[j] == True)]  # noqa: E712
+        span = []
+        for grp in (good, poor):
+            lo = len(pair_h)
+            if len(grp) > 1:
+                for a in range(len(grp)):
+                    for c in range(a + 1, len(grp)):
+                        pair_h.append(grp[a]); pair_s.append(grp[c])
+            span.append((lo, len(pair_h)))
+        lo = len(pair_h)
+        if len(good) > 1 and len(poor) > 1:
+            for a in good:
+                for c in poor:
+                    pair_h.append(a); pair_s.append(c)
+        span.append((lo, len(pair_h)))
+        spans.append(span)
+    sc = _score_index_pairs(paths, paths, pair_h, pair_s)[:, :2][:, ::-1]
+    out = [[], [], []]
+    for span in spans:
+        for k, (lo, hi) in enumerate(span):
+            out[k].append(_mean2(sc[lo:hi], is_eliminating_nan)[0])
+    return np.array(out[0]), np.array(out[1]), np.array(out[2])
+
+
+def evaluation_performance_related(gt_fix_vectors, predict_fix_vectors, all_performances, all_allocated_performances):
+    """AiR/utils/evaluation.py:188-359.  Returns (metrics, metrics_std, per_image) with the categories
+    all / right_answer / wrong_answer.  Quirks kept: rows are aggregated in float32; AiR stores
+    (SM with duration, SM w/o duration) in slots 5, 6 but LABELS slot 5 'w/o duration' and slot 6
+    'with duration' (:231-236 vs :321-322) -- the labels below are the reference's."""
+    scores, hpack, ppack, pair_h, pair_s, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    sc = scores.cpu().numpy()
+    hl, pl = hpack.len.cpu().numpy(), ppack.len.cpu().numpy()
+    cats, per_image, o = [[], [], []], [], 0
+    for i, s in enumerate(sizes):
+        rows = [[], [], []]
+        for j in range(s):
+            if hl[pair_h[o + j]] < MIN_LEN_VALID or pl[pair_s[o + j]] < MIN_LEN_VALID:
+                continue                                   # MultiMatch NaN -> pair skipped (:218-219)
+            r = sc[o + j]
+            rows[0].append(r)
+            if all_performances[i][j] == True and all_allocated_performances[i] == True:      # noqa: E712
+                rows[1].append(r)
+            elif all_performances[i][j] == False and all_allocated_performances[i] == False:  # noqa: E712
+                rows[2].append(r)
+        for c in range(3):
+            cats[c].append(np.array(rows[c], dtype=np.float32).reshape(-1, 4))
+        own = rows[1] if all_allocated_performances[i] == True else rows[2]                     # noqa: E712
+        per_image.append([np.nan] * 5 + list(np.array(own).mean(axis=0)) if own else list(np.zeros(9)))
+        o += s
+    m_out, s_out = {}, {}
+    for c, name in enumerate(("all", "right_answer", "wrong_answer")):
+        groups = [g for g in cats[c] if len(g) != 0]
+        allrows = np.concatenate(groups, axis=0)
+        best = np.array([[g[:, 2].min(), g[:, 3].max()] for g in groups], dtype=np.float32)
+        for dst, fn in ((m_out, np.mean), (s_out, np.std)):
+            a, b = fn(allrows, axis=0), fn(best, axis=0)
+            dst[name] = {"MultiMatch": _nan5(),
+                         "ScanMatch": {"w/o duration": a[0], "with duration": a[1]},
+                         "VAME": {"SED": a[2], "STDE": a[3], "SED_best": b[0], "STDE_best": b[1]}}
+    return m_out, s_out, per_image

@@ -260,6 +260,52 @@ def gen_sampling():
     print("sampling goldens written")
 
 
+def gen_air_eval():
+    """AiR's performance-related drivers (AiR/utils/evaluation.py:188-577)."""
+    rng = np.random.default_rng(3)
+    N, S = 5, 6
+    humans = [human_paths(rng, S, 2, 12) for _ in range(N)]
+    humans[1][2] = humans[1][2][:2]                      # MultiMatch-NaN rule
+    perf = [[bool(b) for b in rng.integers(0, 2, S)] for _ in range(N)]
+    perf[3] = [True] * S                                 # no wrong answerers for image 3
+    preds = pred_paths(rng, N, 3, 16)
+    alloc = [bool(b) for b in rng.integers(0, 2, N)]
+    hp, hl = pad([h for img in humans for h in img])
+    pp, pl = pad(preds)
+    out = dict(human=hp.reshape(N, S, -1, 3), human_len=hl.reshape(N, S), pred=pp, pred_len=pl,
+               perf=np.array(perf), alloc=np.array(alloc))
+    ns = refload.load_reference("AiR")
+    ev = ns.evaluation
+    SM = ns.scanmatch.ScanMatch
+    cfg = dict(Xres=320, Yres=240, Xbin=16, Ybin=12, Offset=(0, 0), Threshold=3.5)
+    wd_obj, wod_obj = SM(TempBin=50, **cfg), SM(**cfg)
+    gt_struct = [[to_struct(h) for h in img] for img in humans]
+    pr_struct = [to_struct(p) for p in preds]
+    for given in (True, False):
+        same, diff, flag = ev.pairs_eval_scanmatch_performance_related(gt_struct, pr_struct, wd_obj, wod_obj, perf, given)
+        out["pesm_same_%d" % given], out["pesm_diff_%d" % given], out["pesm_flag_%d" % given] = same, diff, flag
+    g, p, gp = ev.gtpairs_eval_scanmatch_performance_related(gt_struct, wd_obj, wod_obj, perf)
+    out["gtp_good"], out["gtp_poor"], out["gtp_good_vs_poor"] = g, p, gp
+    # evaluation_performance_related filters its lists with `_ != []` (AiR/utils/evaluation.py:277-279),
+    # which numpy >= 2 rejects (shape mismatch raises instead of returning a scalar).  To pin the
+    # aggregation anyway the function is re-executed IN MEMORY with those three comparisons spelt
+    # `len(_) != 0` (what numpy 1.x evaluated them to); nothing else is touched, nothing is written.
+    import inspect
+    src = inspect.getsource(ev.evaluation_performance_related).replace("if _ != []]", "if len(_) != 0]")
+    assert src.count("if len(_) != 0]") == 3
+    scope = dict(ev.__dict__)
+    exec(compile(src, "<evaluation_performance_related, numpy-2 shim>", "exec"), scope)
+    m, s, per = scope["evaluation_performance_related"](gt_struct, pr_struct, perf, alloc)
+    cats = ["all", "right_answer", "wrong_answer"]
+    flat = lambda d: np.array([[d[c]["ScanMatch"]["w/o duration"], d[c]["ScanMatch"]["with duration"],
+                                d[c]["VAME"]["SED"], d[c]["VAME"]["STDE"], d[c]["VAME"]["SED_best"],
+                                d[c]["VAME"]["STDE_best"]] for c in cats])
+    out["epr_mean"], out["epr_std"] = flat(m), flat(s)
+    out["epr_per_image"] = np.array(per, dtype=np.float64)[:, 5:]
+    np.savez_compressed(os.path.join(HERE, "eval_air.npz"), **out)
+    print("air eval goldens written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("scoring", "all"):
@@ -268,6 +314,9 @@ if __name__ == "__main__":
         gen_eval()
     if what in ("sampling", "all"):
         gen_sampling()
+    if what in ("air", "all"):
+        gen_air_eval()
     if what in ("decoder", "all"):
         from make_decoder_goldens import gen_decoder
         gen_decoder()
+

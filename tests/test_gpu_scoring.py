@@ -245,3 +245,27 @@ def test_full_size_properties(S):
     got = out[idx].cpu().numpy()
     assert np.array_equal(got[:, :3], ref[:, :3], equal_nan=True)
     np.testing.assert_allclose(got[:, 3], ref[:, 3], rtol=STDE_RTOL)
+
+
+def test_mirror_air_performance_related_drivers(S, golden_dir):
+    from test_oracle_golden import _air_lists
+    from scanpaths_b200.utils import evaluation as E
+    g = np.load(os.path.join(golden_dir, "eval_air.npz"))
+    humans, preds, perf, alloc = _air_lists(g)
+    for given in (True, False):
+        same, diff, flag = E.pairs_eval_scanmatch_performance_related(humans, preds, None, None, perf, given)
+        np.testing.assert_allclose(same, g["pesm_same_%d" % given], rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(diff, g["pesm_diff_%d" % given], rtol=1e-12, equal_nan=True)
+        assert flag == bool(g["pesm_flag_%d" % given])
+    good, poor, gp = E.gtpairs_eval_scanmatch_performance_related(humans, None, None, perf)
+    np.testing.assert_allclose(good, g["gtp_good"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(poor, g["gtp_poor"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(gp, g["gtp_good_vs_poor"], rtol=1e-12, equal_nan=True)
+    m, s, per = E.evaluation_performance_related(humans, preds, perf, alloc)
+    cats = ["all", "right_answer", "wrong_answer"]
+    flat = lambda d: np.array([[d[c]["ScanMatch"]["w/o duration"], d[c]["ScanMatch"]["with duration"],
+                                d[c]["VAME"]["SED"], d[c]["VAME"]["STDE"], d[c]["VAME"]["SED_best"],
+                                d[c]["VAME"]["STDE_best"]] for c in cats])
+    np.testing.assert_allclose(flat(m), g["epr_mean"], rtol=2e-6)
+    np.testing.assert_allclose(flat(s), g["epr_std"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(np.array(per)[:, 5:], g["epr_per_image"], rtol=1e-12)

@@ -134,3 +134,31 @@ def test_supervised_losses(golden_dir):
         float(g["loss_ce"]), rel=1e-5)
     assert OS.lognormal_nll(g["mu"], g["sigma2"], g["loss_gt_dur"], g["loss_mask"]) == pytest.approx(
         float(g["loss_lognormal"]), rel=1e-5)
+
+
+def _air_lists(g):
+    from golden.make_goldens import to_struct
+    N, S = g["human_len"].shape
+    humans = [[to_struct(g["human"][i, s, :g["human_len"][i, s]]) for s in range(S)] for i in range(N)]
+    preds = [to_struct(g["pred"][i, :g["pred_len"][i]]) for i in range(N)]
+    perf = [[bool(v) for v in row] for row in g["perf"]]
+    alloc = [bool(v) for v in g["alloc"]]
+    return humans, preds, perf, alloc
+
+
+def test_air_performance_related_drivers(golden_dir):
+    g = _load(golden_dir, "eval_air.npz")
+    humans, preds, perf, alloc = _air_lists(g)
+    for given in (True, False):
+        same, diff, flag = O.pairs_eval_scanmatch_performance_related(humans, preds, perf, given)
+        np.testing.assert_allclose(same, g["pesm_same_%d" % given], rtol=1e-13, equal_nan=True)
+        np.testing.assert_allclose(diff, g["pesm_diff_%d" % given], rtol=1e-13, equal_nan=True)
+        assert flag == bool(g["pesm_flag_%d" % given])
+    good, poor, gp = O.gtpairs_eval_scanmatch_performance_related(humans, perf)
+    np.testing.assert_allclose(good, g["gtp_good"], rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(poor, g["gtp_poor"], rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(gp, g["gtp_good_vs_poor"], rtol=1e-13, equal_nan=True)
+    mean, std, per = O.evaluation_performance_related(humans, preds, perf, alloc)
+    np.testing.assert_allclose(mean, g["epr_mean"], rtol=2e-6)       # float32 aggregation in the reference
+    np.testing.assert_allclose(std, g["epr_std"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(per, g["epr_per_image"], rtol=1e-12)
