@@ -187,7 +187,7 @@ int spb_generate_scanpaths(const int32_t *d_actions, const float *d_dur, int64_t
  * baseline_attention.py::prepare_weights builds them from a reference state_dict):
  *   conv weights  fp16 pairs (hi, lo): w * scale = hi + lo / 2^11, rows = output
  *                 channel, K index = (ky*ks + kx)*512 + ci; gate matrices have 2048
- *                 rows ordered [channel block of 64][gate i,f,o,g][64].
+ *                 rows ordered [channel block of 64][half of 32][gate i,f,o,g][32].
  * ---------------------------------------------------------------------- */
 typedef struct spb_decoder_weights {
     const void *wx_hi, *wx_lo;       /* fp16 [2048, 4608]  lstm.*_x                     */

@@ -25,6 +25,13 @@
 //     mid-loop: its values weigh 2^-11).
 //   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator,
 //     warps 2-9 drain/epilogue (each thread: 1 TMEM lane x 128 columns of running totals).
+//   * persistent: grid = #SMs, every CTA walks tiles blockIdx.x, +gridDim.x, ... (column tiles
+//     of one pixel tile are adjacent, so the A tile is shared through L2).  Because the totals
+//     live in registers, TMEM is free again as soon as the last tap is drained: the MMA thread
+//     starts the next tile while the drain warps run the epilogue of the previous one.
+//   * epilogue modes: (0) scale + bias + fp32 store; (1) the whole ConvLSTM cell
+//     (ConvLSTM.forward :39-46): gate pre-activations = GEMM + x-convolution + rank-1 memory
+//     term, sigmoid / tanh, c' = f c + i g, h' = o c' written as the next step's fp16 pair.
 //   * operands staged by TMA with 128-byte swizzle, K-major; kStages-deep mbarrier ring.
 #include <cuda.h>
 
@@ -39,7 +46,8 @@ constexpr int kABytes = kBlockM * kBlockK * 2;            // 16 KB (15 KB writte
 constexpr int kATxBytes = kValidM * kBlockK * 2;          // 15360
 constexpr int kBBytes = kBlockN * kBlockK * 2;            // 32 KB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;    // 96 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kEpiFloats = 2 * (3 * 64 * 9 + 5 * 42);   // fused-cell staging: V tile + spatial halo, <= 2 streams
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiFloats * 4;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 320;
 constexpr int kChunkKB = kE / kBlockK;                   // k-blocks per drained chunk: one filter tap
@@ -114,11 +122,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 
-template <int KS>
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                    ConvGemmArgs a) {
+                    ConvGemmArgs a, int num_tiles, int ntn) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + kStages * kStageBytes;
@@ -126,12 +140,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     auto empty_bar = [&](int s) { return bar0 + 8 * (kStages + s); };
     const uint32_t main_full_bar = bar0 + 8 * (2 * kStages);        // MMA -> drain warps: one tap accumulated
     const uint32_t main_empty_bar = bar0 + 8 * (2 * kStages + 1);   // drain warps -> MMA: accumulator 0 read out
-    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 2);
+    const uint32_t corr_empty_bar = bar0 + 8 * (2 * kStages + 2);   // drain warps -> MMA: accumulator 1 read out
+    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 3);
+    float *epi = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y, img = blockIdx.z;
     constexpr int kNumKB = KS * KS * (kE / kBlockK);
+    constexpr int kNumChunks = kNumKB / kChunkKB;
     constexpr int kPad = KS / 2;
+    constexpr int kMT = kHW / kValidM;   // 10 pixel tiles per image
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
@@ -141,6 +158,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(main_full_bar, 1);
         mbar_init(main_empty_bar, 8);
+        mbar_init(corr_empty_bar, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -154,56 +172,86 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-    const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + n_tile * kBlockN;
-
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            const int y0 = m_tile * 3;
-            for (int kb = 0; kb < kNumKB; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(empty_bar(s), ((kb / kStages) & 1) ^ 1);
-                const int tap = kb / (kE / kBlockK), cb = kb % (kE / kBlockK);
-                const int ky = tap / KS, kx = tap % KS;
-                const uint32_t sa = base + s * kStageBytes;
-                mbar_expect_tx(full_bar(s), 2 * kATxBytes + 2 * kBBytes);
-                tma_load_4d(sa, &tmA_hi, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
-                tma_load_4d(sa + kABytes, &tmA_lo, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
-                tma_load_2d(sa + 2 * kABytes, &tmB_hi, full_bar(s), kb * kBlockK, row_base);
-                tma_load_2d(sa + 2 * kABytes + kBBytes, &tmB_lo, full_bar(s), kb * kBlockK, row_base);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % ntn, m_tile = (tile / ntn) % kMT, img = tile / (ntn * kMT);
+                const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + n_tile * kBlockN;
+                const int y0 = m_tile * 3;
+                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+                    const int tap = kb / (kE / kBlockK), cb = kb % (kE / kBlockK);
+                    const int ky = tap / KS, kx = tap % KS;
+                    const uint32_t sa = base + s * kStageBytes;
+                    mbar_expect_tx(full_bar(s), 2 * kATxBytes + 2 * kBBytes);
+                    tma_load_4d(sa, &tmA_hi, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
+                    tma_load_4d(sa + kABytes, &tmA_lo, full_bar(s), cb * kBlockK, kx - kPad, y0 + ky - kPad, img);
+                    tma_load_2d(sa + 2 * kABytes, &tmB_hi, full_bar(s), kb * kBlockK, row_base);
+                    tma_load_2d(sa + 2 * kABytes + kBBytes, &tmB_lo, full_bar(s), kb * kBlockK, row_base);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t d_main = tmem_base, d_corr = tmem_base + kBlockN;
-            for (int kb = 0; kb < kNumKB; ++kb) {
-                const int s = kb % kStages;
-                const int chunk = kb / kChunkKB, kc = kb % kChunkKB;
-                mbar_wait(full_bar(s), (kb / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = base + s * kStageBytes;
-                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
-                const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
-                // correction products first: they do not touch accumulator 0, which the drain
-                // warps may still be reading at a chunk boundary
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                    umma_f16(d_corr, a_hi + adv, b_lo + adv, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_f16(d_corr, a_lo + adv, b_hi + adv, 1u);
-                }
-                if (kc == 0 && chunk > 0) {
-                    mbar_wait(main_empty_bar, (chunk - 1) & 1);
+            uint32_t it = 0, gch = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const int kc = kb % kChunkKB;
+                    mbar_wait(full_bar(s), (it / kStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
+                    const uint32_t sa = base + s * kStageBytes;
+                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kABytes);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * kABytes), b_lo = umma_desc_sw128(sa + 2 * kABytes + kBBytes);
+                    if (kb == 0) {
+                        // tile boundary: accumulator 0 is released by the last drain of the previous tile,
+                        // accumulator 1 a little later (it is folded into the totals after that drain)
+                        if (gch > 0) {
+                            mbar_wait(main_empty_bar, (gch - 1) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                    umma_f16(d_main, a_hi + adv, b_hi + adv, (kc > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_main, a_hi + adv, b_hi + adv, k > 0 ? 1u : 0u);
+                        }
+                        if (ti > 0) {
+                            mbar_wait(corr_empty_bar, (ti - 1) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_corr, a_hi + adv, b_lo + adv, k > 0 ? 1u : 0u);
+                            umma_f16(d_corr, a_lo + adv, b_hi + adv, 1u);
+                        }
+                    } else {
+                        // correction products first: they do not touch accumulator 0, which the drain
+                        // warps may still be reading at a chunk boundary
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_corr, a_hi + adv, b_lo + adv, 1u);
+                            umma_f16(d_corr, a_lo + adv, b_hi + adv, 1u);
+                        }
+                        if (kc == 0) {
+                            mbar_wait(main_empty_bar, (gch - 1) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_main, a_hi + adv, b_hi + adv, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));            // frees this smem stage once the MMAs have read it
+                    if (kc == kChunkKB - 1) { umma_commit(main_full_bar); ++gch; }   // this tap's partial sum is complete
                 }
-                umma_commit(empty_bar(s));            // frees this smem stage once the MMAs have read it
-                if (kc == kChunkKB - 1) umma_commit(main_full_bar);   // this tap's partial sum is complete
             }
         }
     } else {
@@ -212,49 +260,147 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int half = (warp - 2) >> 2;             // column half: warps 2-5 -> 0, warps 6-9 -> 1
         const int r = q * 32 + lane;
         const bool valid = r < kValidM;
+        const int etid = threadIdx.x - 64;            // 0..255 among the epilogue threads
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * (kBlockN / 2);
-        float tot[kBlockN / 2];
+        uint32_t gch = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % ntn, m_tile = (tile / ntn) % kMT, img = tile / (ntn * kMT);
+            float tot[kBlockN / 2];
 #pragma unroll
-        for (int j = 0; j < kBlockN / 2; ++j) tot[j] = 0.0f;
-        constexpr int kNumChunks = kNumKB / kChunkKB;
-        for (int chunk = 0; chunk < kNumChunks; ++chunk) {
-            mbar_wait(main_full_bar, chunk & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j = 0; j < kBlockN / 2; ++j) tot[j] = 0.0f;
+            for (int chunk = 0; chunk < kNumChunks; ++chunk, ++gch) {
+                mbar_wait(main_full_bar, gch & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < kBlockN / 2; c += 32) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(lane_addr + c, v0);
+                    tmem_ld16(lane_addr + c + 16, v1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        tot[c + j] += __uint_as_float(v0[j]);
+                        tot[c + 16 + j] += __uint_as_float(v1[j]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(main_empty_bar) : "memory");
+            }
+            // the last main_full commit also covers every correction MMA of this tile: fold accumulator 1
+            // into the totals and hand TMEM back, then run the epilogue from registers
 #pragma unroll
             for (int c = 0; c < kBlockN / 2; c += 32) {
                 uint32_t v0[16], v1[16];
-                tmem_ld16(lane_addr + c, v0);
-                tmem_ld16(lane_addr + c + 16, v1);
+                tmem_ld16(lane_addr + kBlockN + c, v0);
+                tmem_ld16(lane_addr + kBlockN + c + 16, v1);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    tot[c + j] += __uint_as_float(v0[j]);
-                    tot[c + 16 + j] += __uint_as_float(v1[j]);
+                    tot[c + j] += __uint_as_float(v0[j]) * (1.0f / kLoScale);
+                    tot[c + 16 + j] += __uint_as_float(v1[j]) * (1.0f / kLoScale);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(main_empty_bar) : "memory");
-        }
-        // the last main_full commit also covers every correction MMA issued before it
-        const int64_t orow = ((int64_t)img * kHW + m_tile * kValidM + r) * a.ldo + n_tile * kBlockN + half * (kBlockN / 2);
-        const int bias0 = row_base + half * (kBlockN / 2);
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(corr_empty_bar) : "memory");
+
+            const int p = m_tile * kValidM + r;                       // pixel of this thread
+            const int64_t pix = (int64_t)img * kHW + p;
+            if (MODE == 0) {
+                if (valid) {
+                    const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + n_tile * kBlockN + half * (kBlockN / 2);
+                    float *dst = a.out + pix * a.ldo + n_tile * kBlockN + half * (kBlockN / 2);
 #pragma unroll
-        for (int c = 0; c < kBlockN / 2; c += 16) {
-            uint32_t vc[16];
-            tmem_ld16(lane_addr + kBlockN + c, vc);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (valid) {
-                float o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float v = (tot[c + j] + __uint_as_float(vc[j]) * (1.0f / kLoScale)) * a.inv_scale;
-                    if (a.bias) v += a.bias[bias0 + c + j];
-                    o[j] = v;
+                    for (int c = 0; c < kBlockN / 2; c += 4) {
+                        float4 o;
+                        o.x = tot[c] * a.inv_scale; o.y = tot[c + 1] * a.inv_scale;
+                        o.z = tot[c + 2] * a.inv_scale; o.w = tot[c + 3] * a.inv_scale;
+                        if (a.bias) {
+                            o.x += a.bias[row_base + c]; o.y += a.bias[row_base + c + 1];
+                            o.z += a.bias[row_base + c + 2]; o.w += a.bias[row_base + c + 3];
+                        }
+                        *reinterpret_cast<float4 *>(dst + c) = o;
+                    }
                 }
-                float4 *dst = reinterpret_cast<float4 *>(a.out + orow + c);
+            } else {
+                // ---- fused ConvLSTM cell.  n_tile is the 64-channel block; this thread owns channels
+                // ch0 .. ch0+31 of pixel p; tot[g*32 + j] is gate g (i, f, o, g) of channel ch0 + j.
+                const int S = a.n_streams;
+                const int ch0 = n_tile * 64 + half * 32;
+                const int y0 = m_tile * 3;
+                float *Vs = epi;                                   // [S][3][64][9]
+                float *Hs = epi + S * 3 * 64 * 9;                  // [S][5][42] spatial halo, zero outside the image
+                named_bar_sync(1, 256);                            // previous tile's epilogue is done with the staging area
+                for (int i = etid; i < S * 3 * 64 * 9; i += 256) {
+                    const int sg = i / (64 * 9), rem = i - sg * (64 * 9);      // sg = s*3 + g
+                    Vs[i] = a.V[((int64_t)img * S * 3 + sg) * (kE * 9) + n_tile * 64 * 9 + rem];
+                }
+                for (int i = etid; i < S * 5 * 42; i += 256) {
+                    const int st = i / 210, rem = i - st * 210, hy = rem / 42, hx = rem - hy * 42;
+                    const int yy = y0 - 1 + hy, xx = hx - 1;
+                    Hs[i] = (yy >= 0 && yy < kH && xx >= 0 && xx < kW) ? a.sp_mem[((int64_t)img * S + st) * kHW + yy * kW + xx]
+                                                                     : 0.0f;
+                }
+                named_bar_sync(1, 256);
+                if (valid) {
+                    const int ly = r / kW, lx = r - ly * kW;       // position inside the 3 x 40 tile
+                    float spn[2][9];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    for (int st = 0; st < 2; ++st)
+#pragma unroll
+                        for (int t9 = 0; t9 < 9; ++t9)
+                            spn[st][t9] = (st < S) ? Hs[st * 210 + (ly + t9 / 3) * 42 + lx + t9 % 3] : 0.0f;
+                    const float *xg = a.xg + pix * kGateCols + n_tile * kBlockN + half * (kBlockN / 2);
+                    float *cptr = a.c + pix * kE + ch0;
+                    __half *hhi = a.h_out_hi + pix * kE + ch0, *hlo = a.h_out_lo + pix * kE + ch0;
+#pragma unroll
+                    for (int j0 = 0; j0 < 32; j0 += 4) {
+                        const float4 xi = *reinterpret_cast<const float4 *>(xg + j0);
+                        const float4 xf = *reinterpret_cast<const float4 *>(xg + 32 + j0);
+                        const float4 xo = *reinterpret_cast<const float4 *>(xg + 64 + j0);
+                        const float4 xm = *reinterpret_cast<const float4 *>(xg + 96 + j0);
+                        const float4 cv = *reinterpret_cast<const float4 *>(cptr + j0);
+                        const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+                        const float xov[4] = {xo.x, xo.y, xo.z, xo.w}, xmv[4] = {xm.x, xm.y, xm.z, xm.w};
+                        const float cold[4] = {cv.x, cv.y, cv.z, cv.w};
+                        float cn[4];
+                        __half hh[4], hl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j0 + e;
+                            float pi = xiv[e] + tot[j] * a.inv_scale;
+                            float pf = xfv[e] + tot[32 + j] * a.inv_scale;
+                            float po = xov[e] + tot[64 + j] * a.inv_scale;
+                            const float pm = xmv[e] + tot[96 + j] * a.inv_scale;
+                            for (int st = 0; st < S; ++st) {
+                                const float *v = Vs + (st * 3 * 64 + half * 32 + j) * 9;
+                                float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+#pragma unroll
+                                for (int t9 = 0; t9 < 9; ++t9) {
+                                    const float sv = spn[st][t9];
+                                    r0 = fmaf(v[t9], sv, r0);
+                                    r1 = fmaf(v[64 * 9 + t9], sv, r1);
+                                    r2 = fmaf(v[2 * 64 * 9 + t9], sv, r2);
+                                }
+                                pi += r0; pf += r1; po += r2;
+                            }
+                            const float gi = sigmoidf_acc(pi), gf = sigmoidf_acc(pf), go = sigmoidf_acc(po);
+                            const float gg = tanhf(pm);
+                            cn[e] = gf * cold[e] + gi * gg;
+                            const float hv = go * cn[e];
+                            hh[e] = __float2half_rn(hv);
+                            hl[e] = __float2half_rn((hv - __half2float(hh[e])) * kLoScale);
+                        }
+                        *reinterpret_cast<float4 *>(cptr + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        *reinterpret_cast<uint2 *>(hhi + j0) =
+                            make_uint2((uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16),
+                                       (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16));
+                        *reinterpret_cast<uint2 *>(hlo + j0) =
+                            make_uint2((uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16),
+                                       (uint32_t)__half_as_ushort(hl[2]) | ((uint32_t)__half_as_ushort(hl[3]) << 16));
+                    }
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -313,10 +459,6 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
         set_error("conv_gemm_tc: cols must be a multiple of %d, ldo of 4, ks 3 or 5", kBlockN);
         return SPB_ERR_ARG;
     }
-    if (a.n_images > 65535) {
-        set_error("conv_gemm_tc: at most 65535 images per launch");
-        return SPB_ERR_ARG;
-    }
     if (get_encode() == nullptr) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled not available from the driver");
         return SPB_ERR_CUDA;
@@ -331,13 +473,23 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
     }
-    dim3 grid(a.cols / kBlockN, kHW / kValidM, a.n_images);
-    if (a.ks == 3) {
-        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        conv_gemm_tc_kernel<3><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+    const int ntn = a.cols / kBlockN;
+    const int num_tiles = ntn * (kHW / kValidM) * a.n_images;
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
+    if (a.mode == 1) {
+        if (a.ks != 3 || a.cols != kGateCols || !a.xg || !a.c || !a.V || !a.sp_mem || !a.h_out_hi || !a.h_out_lo ||
+            a.n_streams < 1 || a.n_streams > 2 || a.h_out_hi == a.a_hi) {
+            set_error("conv_gemm_tc: bad arguments for the fused ConvLSTM-cell epilogue");
+            return SPB_ERR_ARG;
+        }
+        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        conv_gemm_tc_kernel<3, 1><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a, num_tiles, ntn);
+    } else if (a.ks == 3) {
+        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        conv_gemm_tc_kernel<3, 0><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a, num_tiles, ntn);
     } else {
-        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        conv_gemm_tc_kernel<5><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
+        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        conv_gemm_tc_kernel<5, 0><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, a, num_tiles, ntn);
     }
     SPB_LAUNCH_CHECK();
     return SPB_OK;

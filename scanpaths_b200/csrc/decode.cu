@@ -233,10 +233,10 @@ lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, co
     const int64_t n = np / kHW;
     const int p = (int)(np - n * kHW);
     const int py = p / kW, px = p - py * kW;
-    const int64_t g0 = np * kGateCols + (ch >> 6) * 256 + (ch & 63);
+    const int64_t g0 = np * kGateCols + gate_col(ch, 0);
     float pre[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) pre[g] = xg[g0 + g * 64] + acc[g0 + g * 64];
+    for (int g = 0; g < 4; ++g) pre[g] = xg[g0 + g * 32] + acc[g0 + g * 32];
     for (int s = 0; s < S; ++s) {
         const float *sp = sp_mem + (n * S + s) * kHW;
         const float *v = V + ((n * S + s) * 3) * (int64_t)(kE * 9) + ch * 9;
@@ -265,6 +265,71 @@ lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, co
     __half hh, hl;
     split_one(go * cn, hh, hl);
     h_hi[idx] = hh; h_lo[idx] = hl;
+}
+
+// Bandwidth-shaped version used on the tensor-core path: one block per (image, 3-row pixel tile),
+// one thread per channel.  The thread keeps its 27 rank-1 weights per stream in registers for all
+// 120 pixels, the tile's spatial-memory halo sits in shared memory, and every global access is a
+// fully coalesced 128-byte line per warp (acc / xg: 4 gate segments of 32 channels, gate_col order).
+// Algorithmic HBM traffic: 26.8 MB per image-step (acc 9.8 + xg 9.8 + c 2.4 r + 2.4 w + h 2.4).
+__global__ void __launch_bounds__(512)
+lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ xg, const float *__restrict__ V,
+                       const float *__restrict__ sp_mem, float *__restrict__ c, __half *__restrict__ h_hi,
+                       __half *__restrict__ h_lo, int S) {
+    __shared__ float halo[2][5][42];
+    const int64_t n = blockIdx.y;
+    const int m_tile = blockIdx.x, y0 = m_tile * 3;
+    const int ch = threadIdx.x;
+    for (int i = threadIdx.x; i < S * 210; i += blockDim.x) {
+        const int st = i / 210, rem = i - st * 210, hy = rem / 42, hx = rem - hy * 42;
+        const int yy = y0 - 1 + hy, xx = hx - 1;
+        halo[st][hy][hx] = (yy >= 0 && yy < kH && xx >= 0 && xx < kW) ? sp_mem[(n * S + st) * kHW + yy * kW + xx] : 0.0f;
+    }
+    float v[2][3][9];
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9)
+                v[st][g][t9] = (st < S) ? V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9] : 0.0f;
+    __syncthreads();
+    const int gc = gate_col(ch, 0);
+    const int64_t p0 = n * kHW + (int64_t)m_tile * 120;
+#pragma unroll 2
+    for (int r = 0; r < 120; ++r) {
+        const int64_t pix = p0 + r;
+        const int ly = r / kW, lx = r - ly * kW;
+        const float *ap = acc + pix * kGateCols + gc, *xp = xg + pix * kGateCols + gc;
+        float pre0 = ap[0] + xp[0], pre1 = ap[32] + xp[32], pre2 = ap[64] + xp[64];
+        const float pre3 = ap[96] + xp[96];
+        const float cold = c[pix * kE + ch];
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+            if (st < S) {
+                float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    const float sv = halo[st][ly + t9 / 3][lx + t9 % 3];
+                    r0 = fmaf(v[st][0][t9], sv, r0);
+                    r1 = fmaf(v[st][1][t9], sv, r1);
+                    r2 = fmaf(v[st][2][t9], sv, r2);
+                }
+                pre0 += r0; pre1 += r1; pre2 += r2;
+            }
+        }
+        // sigmoid(x) = 1/(1+e^-x), tanh(x) = 1 - 2/(1+e^2x) on the SFU (ex2.approx + correctly rounded
+        // reciprocal): absolute error < 3e-7, no divisions -- keeps this kernel HBM-bound
+        const float gi = __frcp_rn(1.0f + __expf(-pre0));
+        const float gf = __frcp_rn(1.0f + __expf(-pre1));
+        const float go = __frcp_rn(1.0f + __expf(-pre2));
+        const float gg = 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * pre3));
+        const float cn = gf * cold + gi * gg;
+        c[pix * kE + ch] = cn;
+        __half hh, hl;
+        split_one(go * cn, hh, hl);
+        h_hi[pix * kE + ch] = hh; h_lo[pix * kE + ch] = hl;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -477,7 +542,7 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 
 // ---------------------------------------------------------------------------
 struct Workspace {
-    __half *vf_hi, *vf_lo, *h_hi, *h_lo;
+    __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2];
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem;
     int64_t bytes;
@@ -494,8 +559,10 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     const int cap = steps + 1;
     w.vf_hi = (__half *)take(N * kHW * kE * 2);
     w.vf_lo = (__half *)take(N * kHW * kE * 2);
-    w.h_hi = (__half *)take(N * kHW * kE * 2);
-    w.h_lo = (__half *)take(N * kHW * kE * 2);
+    for (int b = 0; b < 2; ++b) {      // ping-pong: the fused cell writes h(t+1) while other tiles still read h(t)
+        w.h_hi[b] = (__half *)take(N * kHW * kE * 2);
+        w.h_lo[b] = (__half *)take(N * kHW * kE * 2);
+    }
     w.vfmean = (float *)take(N * kHW * 4);
     w.xg = (float *)take(N * kHW * kGateCols * 4);
     w.c = (float *)take(N * kHW * kE * 4);
@@ -599,8 +666,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         SPB_TRY(conv_gemm(a, tc, s));
     }
     prof_end(s);
-    SPB_CUDA(cudaMemsetAsync(ws.h_hi, 0, NP * kE * 2, s));
-    SPB_CUDA(cudaMemsetAsync(ws.h_lo, 0, NP * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.h_hi[0], 0, NP * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.h_lo[0], 0, NP * kE * 2, s));
     SPB_CUDA(cudaMemsetAsync(ws.c, 0, NP * kE * 4, s));
 
     auto feedback_tail = [&](int list_index) -> int {
@@ -633,23 +700,35 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
                              ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
         prof_end(s);
-        // 3x3 gate convolutions of h
+        // 3x3 gate convolutions of h + ConvLSTM cell (fused into the GEMM epilogue on the tensor-core path)
+        const int cur = t & 1, nxt = cur ^ 1;
         prof_begin(kTagConvH, s);
         {
-            ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr, kGateCols,
-                           nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
+            ConvGemmArgs a{ws.h_hi[cur], ws.h_lo[cur], (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr,
+                           kGateCols, nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
+            if (io->use_tensor_cores == 2) {   // experimental: cell fused into the GEMM epilogue (slower)
+                a.mode = 1; a.xg = ws.xg; a.c = ws.c; a.V = ws.V; a.sp_mem = ws.sp_mem; a.n_streams = S;
+                a.h_out_hi = ws.h_hi[nxt]; a.h_out_lo = ws.h_lo[nxt];
+            }
             SPB_TRY(conv_gemm(a, tc, s));
         }
         prof_end(s);
-        prof_begin(kTagCell, s);
-        lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi,
-                                                                         ws.h_lo, N, S);
-        SPB_LAUNCH_CHECK();
-        prof_end(s);
+        if (io->use_tensor_cores != 2) {
+            prof_begin(kTagCell, s);
+            if (tc) {
+                lstm_cell_tiled_kernel<<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c,
+                                                                                   ws.h_hi[nxt], ws.h_lo[nxt], S);
+            } else {
+                lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c,
+                                                                                 ws.h_hi[nxt], ws.h_lo[nxt], N, S);
+            }
+            SPB_LAUNCH_CHECK();
+            prof_end(s);
+        }
         // 5x5 layer(s) on the new h
         prof_begin(kTagConvP, s);
         {
-            ConvGemmArgs a{ws.h_hi, ws.h_lo, (const __half *)w->wp_hi, (const __half *)w->wp_lo, io->d_w_row_base,
+            ConvGemmArgs a{ws.h_hi[nxt], ws.h_lo[nxt], (const __half *)w->wp_hi, (const __half *)w->wp_lo, io->d_w_row_base,
                            (int64_t)w->n_weight_sets * kE, w->bias_p, ws.feat, (int64_t)HD * kE, (int)N, HD * kE, 5,
                            w->inv_scale_p};
             SPB_TRY(conv_gemm(a, tc, s));

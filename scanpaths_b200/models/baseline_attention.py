@@ -54,9 +54,11 @@ def _conv_to_gemm(w):
 
 
 def _interleave_gates(mats):
-    """4 x [512, K] (i, f, o, g) -> [2048, K] rows ordered [channel block of 64][gate][64]."""
+    """4 x [512, K] (i, f, o, g) -> [2048, K] rows ordered [64-channel block][32-channel half][gate][32]
+    (csrc/decoder.cuh::gate_col): one epilogue thread of the tensor-core kernel then owns all four
+    gates of 32 channels of its pixel."""
     g = torch.stack(mats, 0)                                  # [4, 512, K]
-    return g.view(4, 8, 64, -1).permute(1, 0, 2, 3).reshape(2048, -1).contiguous()
+    return g.view(4, 8, 2, 32, -1).permute(1, 2, 0, 3, 4).reshape(2048, -1).contiguous()
 
 
 def prepare_weights(sd, task: str, device):
@@ -126,7 +128,7 @@ class CudaDecoder:
         self.lib = _lib.load()
         self.task, self.steps, self.wave = task, int(steps), int(wave)
         self.device = torch.device(device)
-        self.use_tensor_cores = bool(use_tensor_cores)
+        self.use_tensor_cores = int(use_tensor_cores)     # 0 SIMT check path, 1 tcgen05, 2 tcgen05 + fused cell (experimental)
         self.tensors, self.w = prepare_weights(state_dict, task, self.device)
         self.heads = int(self.w.n_heads)
         self._ws, self._ws_n = None, 0
@@ -167,7 +169,7 @@ class CudaDecoder:
             m_w = mu if dense else torch.empty((HD, n, T), dtype=torch.float32, device=dev)
             s_w = s2 if dense else torch.empty((HD, n, T), dtype=torch.float32, device=dev)
             a_w = amap if dense else torch.empty((HD, n, T, HW), dtype=torch.float32, device=dev)
-            io = DecoderIO(n, T, 1 if self.use_tensor_cores else 0, 0, vf[n0:n1].data_ptr(),
+            io = DecoderIO(n, T, self.use_tensor_cores, 0, vf[n0:n1].data_ptr(),
                            att[n0:n1].data_ptr() if att is not None else None,
                            rows[n0:n1].data_ptr() if rows is not None else None, ws_ptr, ws_bytes, p_w.data_ptr(),
                            m_w.data_ptr(), s_w.data_ptr(), a_w.data_ptr())

@@ -50,7 +50,8 @@ class ScanpathPipeline:
                 self._pairs.pop(next(iter(self._pairs)))
         return self._pairs[key]
 
-    def run(self, visual_feature, attention_maps=None, tasks=None, keep_scores=False, valid_min_len=0):
+    def run(self, visual_feature, attention_maps=None, tasks=None, keep_scores=False, valid_min_len=0,
+            keep_paths=False):
         """visual_feature [N,512,30,40] f32 on the device or in (pinned) host memory.
         Returns dict: table [HD, K, N, 11] f32 (pairs_eval layout per sample), reward [HD, K, N] f64,
         metrics (the `evaluation` aggregate over all pairs) and optionally the raw scores."""
@@ -61,6 +62,7 @@ class ScanpathPipeline:
         reward = torch.empty((HD, K, N), dtype=torch.float64, device=dev)
         scores_all = torch.empty((HD, K, N, Sn, 4), dtype=torch.float64, device=dev) if keep_scores else None
         acc = torch.zeros((HD, 12), dtype=torch.float64, device=dev)   # sum, sumsq (4 each), best sums/sumsq (2+2)
+        paths = [] if keep_paths else None
         host_in = not visual_feature.is_cuda
         for n0 in range(0, N, self.wave):
             n1 = min(N, n0 + self.wave)
@@ -91,9 +93,13 @@ class ScanpathPipeline:
                 acc[hd, 10] += (sed_best * sed_best).sum(); acc[hd, 11] += (stde_best * stde_best).sum()
                 if keep_scores:
                     scores_all[hd, :, n0:n1] = sc.view(K, n, Sn, 4)
+                if keep_paths:
+                    paths.append((hd, n0, n1, smp))
         out = {"table": table, "reward": reward, "acc": acc, "n_pairs": K * N * Sn, "n_groups": K * N}
         if keep_scores:
             out["scores"] = scores_all
+        if keep_paths:
+            out["paths"] = paths
         return out
 
     @staticmethod

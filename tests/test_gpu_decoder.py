@@ -108,10 +108,12 @@ def _decode_case(name, use_tc, golden_dir, steps=None):
 
 
 @pytest.mark.parametrize("name", ["coco", "air", "osie"])
-@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
+    """use_tc: 0 = SIMT fp32 check kernels, 1 = tcgen05 (product path), 2 = tcgen05 with the ConvLSTM
+    cell fused into the GEMM epilogue (experimental variant, kept verified)."""
     worst = _decode_case(name, use_tc, golden_dir)
-    print(name, "tc" if use_tc else "simt", worst)
+    print(name, ["simt", "tc", "tc-fused"][use_tc], worst)
     for k, v in worst.items():
         if k.endswith("ref_f32_prob"):
             continue

@@ -1,0 +1,91 @@
+"""End-to-end pipeline (decode -> sample -> prep -> score -> reduce) against the oracle:
+the sampled scanpaths are read back and re-scored / re-aggregated on the CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(task, N, K, Sn, T, wave, seed=0):
+    from scanpaths_b200 import build
+    build.build_library()
+    from scanpaths_b200.pipeline import ScanpathPipeline
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    sys_path_hack = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path_hack)
+    from bench import synth_humans
+    dev = torch.device("cuda")
+    pipe = ScanpathPipeline(random_state_dict(task, seed), task, T, K, 1, dev, wave, seed=77)
+    hx, hl = synth_humans(N, Sn, 5, lo=2, hi=12)
+    pipe.set_humans(hx, hl)
+    if task == "OSIE":
+        vf, att = synthetic_features(N, seed), None
+    else:
+        vf, att = synthetic_features(N, seed, attention=True)
+    return pipe, vf, att, hx, hl
+
+
+@pytest.mark.parametrize("task,wave", [("OSIE", 2), ("AiR", 3)])
+def test_pipeline_table_and_metrics_match_oracle(task, wave):
+    from oracle import c_scoring as CO
+    from oracle import scoring as O
+    from golden.make_goldens import to_struct
+    N, K, Sn, T = 5, 4, 6, 5
+    pipe, vf, att, hx, hl = _setup(task, N, K, Sn, T, wave)
+    out = pipe.run(vf.cuda(), None if att is None else att.cuda(), keep_scores=True, keep_paths=True, valid_min_len=3)
+    torch.cuda.synchronize()
+    HD = pipe.decoder.heads
+    assert out["table"].shape == (HD, K, N, 11) and out["reward"].shape == (HD, K, N)
+    humans = [[to_struct(hx[i, s, :hl[i, s]]) for s in range(Sn)] for i in range(N)]
+    for hd, n0, n1, smp in out["paths"]:
+        n = n1 - n0
+        xyd = smp["xyd"].cpu().numpy(); lens = smp["len"].cpu().numpy()
+        # 1. raw scores of this wave vs the C oracle on the very same sampled paths
+        ha = hx.reshape(N * Sn, -1, 3).copy(); ha[..., 2] *= 1000.0
+        pa = xyd.copy(); pa[..., 2] *= 1000.0
+        gi = np.array([(n0 + i) * Sn + s for k in range(K) for i in range(n) for s in range(Sn)])
+        pi = np.array([k * n + i for k in range(K) for i in range(n) for s in range(Sn)])
+        ref = CO.score_pairs(ha, hl.reshape(-1), pa, lens, gi, pi).reshape(K, n, Sn, 4)
+        got = out["scores"][hd, :, n0:n1].cpu().numpy()
+        assert np.array_equal(got[..., :3], ref[..., :3], equal_nan=True)
+        np.testing.assert_allclose(got[..., 3], ref[..., 3], rtol=1e-12)
+        # 2. the reduced table vs the oracle's pairs_eval on the same lists (per sample k)
+        for k in range(K):
+            preds = [to_struct(xyd[k * n + i, :lens[k * n + i]]) for i in range(n)]
+            pe = O.pairs_eval(humans[n0:n1], preds)
+            tab = out["table"][hd, k, n0:n1].cpu().numpy().astype(np.float64)
+            np.testing.assert_allclose(tab[:, 5:], pe[:, 5:], rtol=1e-6, equal_nan=True)
+            rew = out["reward"][hd, k, n0:n1].cpu().numpy()
+            exp = 2.0 / (1.0 / pe[:, 5] + 1.0 / pe[:, 6])
+            np.testing.assert_allclose(rew, exp, rtol=1e-6, equal_nan=True)
+    # 3. the aggregate equals evaluation() over all (sample, image) entries of head 0
+    all_gt, all_pred = [], []
+    for hd, n0, n1, smp in out["paths"]:
+        if hd != 0:
+            continue
+        xyd = smp["xyd"].cpu().numpy(); lens = smp["len"].cpu().numpy()
+        for k in range(K):
+            for i in range(n1 - n0):
+                all_gt.append(humans[n0 + i]); all_pred.append(to_struct(xyd[k * (n1 - n0) + i, :lens[k * (n1 - n0) + i]]))
+    m_ref, s_ref, _ = O.evaluation(all_gt, all_pred)
+    m, s = pipe.metrics(out, head=0)
+    for grp in ("ScanMatch", "VAME"):
+        for key in m_ref[grp]:
+            assert m[grp][key] == pytest.approx(m_ref[grp][key], rel=1e-10), key
+            assert s[grp][key] == pytest.approx(s_ref[grp][key], rel=1e-6, abs=1e-9), key
+
+
+def test_pipeline_coco_tasks_and_host_input():
+    """COCO variant (per-image 5x5 weights by task id) and pinned-host input features."""
+    N, K, Sn, T = 4, 3, 4, 3
+    pipe, vf, att, hx, hl = _setup("COCO_Search18", N, K, Sn, T, wave=4)
+    tasks = torch.tensor([0, 17, 5, 5])
+    a = pipe.run(vf.cuda(), att.cuda(), tasks, keep_scores=True)
+    pipe.sampler._calls = 0                                # same Philox streams again
+    b = pipe.run(vf.pin_memory(), att.pin_memory(), tasks, keep_scores=True)
+    assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["table"], b["table"])
+    assert torch.isfinite(a["reward"]).all()
