@@ -87,5 +87,6 @@ def test_pipeline_coco_tasks_and_host_input():
     a = pipe.run(vf.cuda(), att.cuda(), tasks, keep_scores=True)
     pipe.sampler._calls = 0                                # same Philox streams again
     b = pipe.run(vf.pin_memory(), att.pin_memory(), tasks, keep_scores=True)
-    assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["table"], b["table"])
+    assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["table"][..., 5:], b["table"][..., 5:])
+    assert torch.isnan(a["table"][..., :5]).all()           # MultiMatch slots are out of scope
     assert torch.isfinite(a["reward"]).all()
