@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--subjects", type=int, default=15)
     ap.add_argument("--wave", type=int, default=256)
+    ap.add_argument("--task", default="OSIE", choices=["OSIE", "AiR", "COCO_Search18"],
+                    help="model variant of the workload (default: the OSIE-shaped configs[1] the metric is quoted on)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
@@ -132,9 +134,10 @@ def run_reference_arm(args, rank):
 
 
 def workload_config(args):
-    return {"workload": "OSIE-shaped decode+sample+score: %d images x %d samples x %d subjects per GPU, T=16, "
+    return {"workload": "%s-shaped decode+sample+score: %d images x %d samples%s x %d subjects per GPU, T=16, "
                         "A=1201, random-init weights with the SURVEY 8d bias calibration" %
-                        (args.images, args.samples, args.subjects),
+                        (args.task, args.images, args.samples, " x 2 heads" if args.task == "AiR" else "", args.subjects),
+            "task": args.task,
             "images_per_gpu": args.images, "samples": args.samples, "subjects": args.subjects,
             "wave": args.wave, "l2": "inputs (%.1f GB of feature maps per step) are larger than L2" %
                                      (args.images * 512 * 1200 * 4 / 1e9)}
@@ -220,15 +223,25 @@ def main():
     from scanpaths_b200.weights import random_state_dict
 
     N, K, S = args.images, args.samples, args.subjects
-    pipe = ScanpathPipeline(random_state_dict("OSIE", 0), "OSIE", T_STEPS, K, 1, dev, args.wave, seed=1234 + rank)
+    pipe = ScanpathPipeline(random_state_dict(args.task, 0), args.task, T_STEPS, K, 1, dev, args.wave, seed=1234 + rank)
+    heads = pipe.decoder.heads                            # AiR: good + poor head -> 2K samples per image
     # synthetic inputs: features relu(N(0,1)) generated on the device in chunks, a pinned host copy for e2e
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     vf_dev = torch.empty((N, 512, 30, 40), dtype=torch.float32, device=dev)
     for n0 in range(0, N, 256):
         n1 = min(N, n0 + 256)
         vf_dev[n0:n1] = torch.randn((n1 - n0, 512, 30, 40), generator=gen, device=dev).clamp_min_(0)
-    hx, hl = synth_humans(N, S, 50 + rank)
+    if args.task == "COCO_Search18":
+        hx, hl = synth_humans(N, S, 50 + rank, lo=2, hi=6)
+    else:
+        hx, hl = synth_humans(N, S, 50 + rank)
     pipe.set_humans(hx, hl)
+    att_dev = tasks_dev = None
+    if args.task != "OSIE":                               # attention map ~ U(0,1)/max, task ~ U{0..17}
+        att_dev = torch.rand((N, 1, 30, 40), generator=gen, device=dev)
+        att_dev /= att_dev.amax(dim=(1, 2, 3), keepdim=True)
+        if args.task == "COCO_Search18":
+            tasks_dev = torch.randint(0, 18, (N,), generator=gen, device=dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -241,7 +254,7 @@ def main():
     def step(vf, repack_humans=False):
         if repack_humans:
             pipe.set_humans(hx_pin, hl_pin)
-        out = pipe.run(vf)
+        out = pipe.run(vf, att_dev, tasks_dev)
         if world > 1:                                     # the one collective of the path: score tables
             gathered[0] = allgather_tables(out["table"], world * N, image_dim=2)
         return out
@@ -276,7 +289,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * N * K * args.steps / (total_ms / 1e3)
+    value = world * N * K * heads * args.steps / (total_ms / 1e3)
     m, s_ = ScanpathPipeline.metrics(out)
 
     # ---- roofline of the dominant kernel: the 3x3 gate convolution (tag 2)
@@ -333,7 +346,7 @@ def main():
         tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * N * K * e_steps / (float(tt.item()) / 1e3), "unit": UNIT,
+        e2e = {"value": world * N * K * heads * e_steps / (float(tt.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(vf_pin.numel() * 4 + hx_pin.numel() * 8 + hl_pin.numel() * 4),
                "d2h_bytes_per_step": int(tab_host.numel() * 4 + acc_host.numel() * 8), "steps": e_steps}
 

@@ -272,11 +272,12 @@ lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, co
 // 120 pixels, the tile's spatial-memory halo sits in shared memory, and every global access is a
 // fully coalesced 128-byte line per warp (acc / xg: 4 gate segments of 32 channels, gate_col order).
 // Algorithmic HBM traffic: 26.8 MB per image-step (acc 9.8 + xg 9.8 + c 2.4 r + 2.4 w + h 2.4).
-__global__ void __launch_bounds__(512)
+template <int S>
+__global__ void __launch_bounds__(512, S == 1 ? 2 : 1)
 lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ xg, const float *__restrict__ V,
                        const float *__restrict__ sp_mem, float *__restrict__ c, __half *__restrict__ h_hi,
-                       __half *__restrict__ h_lo, int S) {
-    __shared__ float halo[2][5][42];
+                       __half *__restrict__ h_lo) {
+    __shared__ float halo[S][5][42];
     const int64_t n = blockIdx.y;
     const int m_tile = blockIdx.x, y0 = m_tile * 3;
     const int ch = threadIdx.x;
@@ -285,18 +286,18 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
         const int yy = y0 - 1 + hy, xx = hx - 1;
         halo[st][hy][hx] = (yy >= 0 && yy < kH && xx >= 0 && xx < kW) ? sp_mem[(n * S + st) * kHW + yy * kW + xx] : 0.0f;
     }
-    float v[2][3][9];
+    float v[S][3][9];
 #pragma unroll
-    for (int st = 0; st < 2; ++st)
+    for (int st = 0; st < S; ++st)
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9)
-                v[st][g][t9] = (st < S) ? V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9] : 0.0f;
+                v[st][g][t9] = V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9];
     __syncthreads();
     const int gc = gate_col(ch, 0);
     const int64_t p0 = n * kHW + (int64_t)m_tile * 120;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < 120; ++r) {
         const int64_t pix = p0 + r;
         const int ly = r / kW, lx = r - ly * kW;
@@ -305,18 +306,16 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
         const float pre3 = ap[96] + xp[96];
         const float cold = c[pix * kE + ch];
 #pragma unroll
-        for (int st = 0; st < 2; ++st) {
-            if (st < S) {
-                float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+        for (int st = 0; st < S; ++st) {
+            float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
 #pragma unroll
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    const float sv = halo[st][ly + t9 / 3][lx + t9 % 3];
-                    r0 = fmaf(v[st][0][t9], sv, r0);
-                    r1 = fmaf(v[st][1][t9], sv, r1);
-                    r2 = fmaf(v[st][2][t9], sv, r2);
-                }
-                pre0 += r0; pre1 += r1; pre2 += r2;
+            for (int t9 = 0; t9 < 9; ++t9) {
+                const float sv = halo[st][ly + t9 / 3][lx + t9 % 3];
+                r0 = fmaf(v[st][0][t9], sv, r0);
+                r1 = fmaf(v[st][1][t9], sv, r1);
+                r2 = fmaf(v[st][2][t9], sv, r2);
             }
+            pre0 += r0; pre1 += r1; pre2 += r2;
         }
         // sigmoid(x) = 1/(1+e^-x), tanh(x) = 1 - 2/(1+e^2x) on the SFU (ex2.approx + correctly rounded
         // reciprocal): absolute error < 3e-7, no divisions -- keeps this kernel HBM-bound
@@ -716,8 +715,12 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         if (io->use_tensor_cores != 2) {
             prof_begin(kTagCell, s);
             if (tc) {
-                lstm_cell_tiled_kernel<<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c,
-                                                                                   ws.h_hi[nxt], ws.h_lo[nxt], S);
+                if (S == 1)
+                    lstm_cell_tiled_kernel<1><<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(
+                        ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
+                else
+                    lstm_cell_tiled_kernel<2><<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(
+                        ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
             } else {
                 lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c,
                                                                                  ws.h_hi[nxt], ws.h_lo[nxt], N, S);

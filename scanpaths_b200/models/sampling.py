@@ -128,3 +128,18 @@ class Sampling():
                                                   _lib.ptr(out["len"]), _lib.current_stream()),
                        "spb_generate_scanpaths")
         return out
+
+
+def predictions_to_records(sampled, img_names, n_images):
+    """The prediction records test.py:135-148 dumps to JSON, built from a packed ``sample_paths`` result
+    (sample-major order k*N + image) with one device->host read: list of dicts
+    {name, repeat_id, X, Y, T (ms), length}."""
+    xyd = sampled["xyd"].cpu().numpy()
+    lens = sampled["len"].cpu().numpy()
+    out = []
+    for idx in range(xyd.shape[0]):
+        k, n = divmod(idx, n_images)
+        L = int(lens[idx])
+        out.append({"name": img_names[n], "repeat_id": k + 1, "X": list(xyd[idx, :L, 0]), "Y": list(xyd[idx, :L, 1]),
+                    "T": list(xyd[idx, :L, 2] * 1000), "length": L})
+    return out
