@@ -204,6 +204,14 @@ typedef struct spb_decoder_weights {
     const float *b_spatial_embed;    /* [1200] */
     const float *w_semantic_embed;   /* [512, 512] */
     const float *b_semantic_embed;   /* [512] */
+    /* composed head (tensor-core path): the 5x5 layer feeds sal_layer_2, sal_layer_3 and drt_layer_1
+     * with no nonlinearity in between, so they collapse into effective kernels on h:          */
+    const float *w23_eff;            /* [n_weight_sets, 25, 512, 2] 5x5 -> (stop map, action map) */
+    const float *b23_eff;            /* [n_weight_sets, 2]  incl. sal_layer_2/3 bias             */
+    const float *wd_eff;             /* [n_weight_sets, 4, 121, 512] 11x11 stride-5 duration conv; variant = */
+                                     /*   2*(window in top row) + (window in left column): taps of drt_layer_1 */
+                                     /*   that fall on the zero padding of the 5x5 output are excluded         */
+    const float *bd_eff;             /* [n_weight_sets, 4]  incl. drt_layer_1 bias               */
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;

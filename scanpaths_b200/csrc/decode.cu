@@ -382,6 +382,129 @@ head_reduce_kernel(const float *__restrict__ feat, int HD, const float *__restri
     }
 }
 
+// ---------------------------------------------------------------------------
+// Composed head (tensor-core path).  predict_head consumes feat = conv5x5(h) only through linear
+// maps (sal_layer_2 / sal_layer_3 1x1, drt_layer_1 7x7 stride 5) before any nonlinearity
+// (OSIE/models/baseline_attention.py:352, :144-150), so the 15.7 GFLOP 5x5 GEMM collapses into
+//   * a 5x5 convolution 512 -> 2 (stop map y2, action map y3): 61 MFLOP per image-step,
+//   * an 11x11 stride-5 convolution 512 -> 1 on 48 windows (4 border variants): 6 MFLOP,
+// with effective kernels composed once in float64 (prepare_weights).  h is read as the same fp16
+// (hi, lo) pair the gate GEMM consumes.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_h4(const __half *hi, const __half *lo, int64_t off, float (&v)[4]) {
+    const uint2 a = *reinterpret_cast<const uint2 *>(hi + off), b = *reinterpret_cast<const uint2 *>(lo + off);
+    const __half2 a0 = *reinterpret_cast<const __half2 *>(&a.x), a1 = *reinterpret_cast<const __half2 *>(&a.y);
+    const __half2 b0 = *reinterpret_cast<const __half2 *>(&b.x), b1 = *reinterpret_cast<const __half2 *>(&b.y);
+    const float2 fa0 = __half22float2(a0), fa1 = __half22float2(a1), fb0 = __half22float2(b0), fb1 = __half22float2(b1);
+    v[0] = fa0.x + fb0.x * (1.0f / kLoScale); v[1] = fa0.y + fb0.y * (1.0f / kLoScale);
+    v[2] = fa1.x + fb1.x * (1.0f / kLoScale); v[3] = fa1.y + fb1.y * (1.0f / kLoScale);
+}
+
+// y2[p], y3[p] for a 3-row pixel tile of one (image, head); weights of the image's set in shared
+// memory ([25][512][2] fp32 = 100 KB); each warp walks its 15 pixels in groups of 3 so that one
+// weight fetch serves three pixels; lane owns channels lane*4 + 128*j.
+constexpr int kMapsPix = 3;
+__global__ void __launch_bounds__(256)
+head_maps_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ w23,
+                 const float *__restrict__ b23, const int32_t *__restrict__ w_row_base, int HD,
+                 float *__restrict__ y2, float *__restrict__ y3) {
+    extern __shared__ float wsm[];                    // [25][512][2]
+    const int64_t nh = blockIdx.y;
+    const int64_t n = nh / HD;
+    const int hd = (int)(nh % HD);
+    const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
+    const float4 *src = reinterpret_cast<const float4 *>(w23 + (int64_t)set * 25 * kE * 2);
+    for (int i = threadIdx.x; i < 25 * kE * 2 / 4; i += blockDim.x) reinterpret_cast<float4 *>(wsm)[i] = src[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p_first = blockIdx.x * 120 + warp * 15;
+    const float bias2 = b23[set * 2], bias3 = b23[set * 2 + 1];
+    for (int g = 0; g < 15; g += kMapsPix) {
+        float a2[kMapsPix], a3[kMapsPix];
+        int py[kMapsPix], px[kMapsPix];
+#pragma unroll
+        for (int u = 0; u < kMapsPix; ++u) {
+            a2[u] = 0.0f; a3[u] = 0.0f;
+            const int p = p_first + g + u;
+            py[u] = p / kW; px[u] = p - py[u] * kW;
+        }
+        for (int tap = 0; tap < 25; ++tap) {
+            const int dy = tap / 5 - 2, dx = tap % 5 - 2;
+            float w[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 *wp = reinterpret_cast<const float4 *>(wsm + (tap * kE + lane * 4 + 128 * j) * 2);
+                const float4 w0 = wp[0], w1 = wp[1];
+                w[j][0] = w0.x; w[j][1] = w0.y; w[j][2] = w0.z; w[j][3] = w0.w;
+                w[j][4] = w1.x; w[j][5] = w1.y; w[j][6] = w1.z; w[j][7] = w1.w;
+            }
+#pragma unroll
+            for (int u = 0; u < kMapsPix; ++u) {
+                const int yy = py[u] + dy, xx = px[u] + dx;
+                if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;     // zero padding of the 5x5 layer
+                const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float hv[4];
+                    load_h4(h_hi, h_lo, base + 128 * j, hv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a2[u] = fmaf(hv[e], w[j][2 * e], a2[u]);
+                        a3[u] = fmaf(hv[e], w[j][2 * e + 1], a3[u]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kMapsPix; ++u) {
+            float s2 = a2[u], s3 = a3[u];
+            for (int o = 16; o > 0; o >>= 1) {
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            }
+            if (lane == 0) {
+                const int64_t o = nh * kHW + p_first + g + u;
+                y2[o] = s2 + bias2;      // head_finish adds nothing more: b2 / b3 are folded into b23_eff
+                y3[o] = s3 + bias3;
+            }
+        }
+    }
+}
+
+// duration pre-activation of the 48 windows: one warp per (image, head, window).
+__global__ void __launch_bounds__(256)
+head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ wd_eff,
+                const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD,
+                float *__restrict__ drt_pre, int64_t n_images) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_images * HD * 48) return;
+    const int o = (int)(warp % 48);
+    const int64_t nh = warp / 48;
+    const int64_t n = nh / HD;
+    const int hd = (int)(nh % HD);
+    const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
+    const int oy = o / 8, ox = o % 8;
+    const int variant = 2 * (oy == 0) + (ox == 0);
+    const float *wv = wd_eff + ((int64_t)set * 4 + variant) * 121 * kE;
+    float acc = 0.0f;
+    for (int tap = 0; tap < 121; ++tap) {
+        const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
+        if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
+        const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float hv[4];
+            load_h4(h_hi, h_lo, base + 128 * j, hv);
+            const float4 w4 = *reinterpret_cast<const float4 *>(wv + tap * kE + lane * 4 + 128 * j);
+            acc = fmaf(hv[0], w4.x, acc); acc = fmaf(hv[1], w4.y, acc);
+            acc = fmaf(hv[2], w4.z, acc); acc = fmaf(hv[3], w4.w, acc);
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) drt_pre[warp] = acc + bd_eff[set * 4 + variant];
+}
+
 __device__ __forceinline__ float block_reduce(float v, float *sh, bool is_max) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int o = 16; o > 0; o >>= 1) {
@@ -401,7 +524,8 @@ __device__ __forceinline__ float block_reduce(float v, float *sh, bool is_max) {
 // One block per (image, head).
 __global__ void __launch_bounds__(256)
 head_finish_kernel(const float *__restrict__ y2, const float *__restrict__ y3, const float *__restrict__ dc,
-                   const float *__restrict__ wd2, spb_decoder_weights w, const float *__restrict__ vfmean,
+                   const float *__restrict__ drt_pre, const float *__restrict__ wd2, spb_decoder_weights w,
+                   const float *__restrict__ vfmean,
                    float *__restrict__ sp_feat, float *__restrict__ probs, float *__restrict__ mu,
                    float *__restrict__ sigma2, float *__restrict__ amap_out, int HD, int64_t n_images, int t,
                    int steps) {
@@ -416,10 +540,12 @@ head_finish_kernel(const float *__restrict__ y2, const float *__restrict__ y3, c
     float *am = amap_out + orow * kHW;
     float s = 0.0f;
     for (int p = threadIdx.x; p < kHW; p += blockDim.x) s += py2[p];
-    const float stop = block_reduce(s, sh, false) / (float)kHW + w.b2;
+    // composed path (drt_pre != NULL): biases are already folded into y2 / y3 / drt_pre
+    const float b2 = drt_pre ? 0.0f : w.b2, b3 = drt_pre ? 0.0f : w.b3;
+    const float stop = block_reduce(s, sh, false) / (float)kHW + b2;
     float mx = stop;
     for (int p = threadIdx.x; p < kHW; p += blockDim.x) {
-        const float a = fmaxf(py3[p] + w.b3, 0.0f);
+        const float a = fmaxf(py3[p] + b3, 0.0f);
         am[p] = a;
         sp_feat[nh * kHW + p] = fmaxf(a * vfmean[n * kHW + p], 0.0f);
         mx = fmaxf(mx, a);
@@ -431,7 +557,9 @@ head_finish_kernel(const float *__restrict__ y2, const float *__restrict__ y3, c
     if (threadIdx.x == 0) pr[0] = expf(stop - mx) / se;
     for (int p = threadIdx.x; p < kHW; p += blockDim.x) pr[1 + p] = expf(am[p] - mx) / se;
     // duration head: t1 = relu(conv7x7 s5 p2 + b), gathered from the per-pixel slot contributions
-    if (threadIdx.x < 48) {
+    if (threadIdx.x < 48 && drt_pre != nullptr) {
+        t1[threadIdx.x] = fmaxf(drt_pre[nh * 48 + threadIdx.x], 0.0f);
+    } else if (threadIdx.x < 48) {
         const int oy = threadIdx.x / 8, ox = threadIdx.x % 8;
         float a = 0.0f;
         for (int ky = 0; ky < 7; ++ky)
@@ -543,7 +671,7 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 struct Workspace {
     __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2];
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
-        *sp_score, *se_score, *sp_mem, *se_mem;
+        *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
     int64_t bytes;
 };
 
@@ -581,6 +709,7 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.se_score = (float *)take(N * S * cap * 4);
     w.sp_mem = (float *)take(N * S * kHW * 4);
     w.se_mem = (float *)take(N * S * kE * 4);
+    w.drt_pre = (float *)take(N * HD * 48 * 4);
     w.bytes = o;
     return w;
 }
@@ -709,7 +838,11 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                 a.mode = 1; a.xg = ws.xg; a.c = ws.c; a.V = ws.V; a.sp_mem = ws.sp_mem; a.n_streams = S;
                 a.h_out_hi = ws.h_hi[nxt]; a.h_out_lo = ws.h_lo[nxt];
             }
-            SPB_TRY(conv_gemm(a, tc, s));
+            if (t == 0 && a.mode == 0) {
+                SPB_CUDA(cudaMemsetAsync(ws.acc, 0, NP * kGateCols * 4, s));   // h(0) = 0: its convolution is exactly 0
+            } else {
+                SPB_TRY(conv_gemm(a, tc, s));
+            }
         }
         prof_end(s);
         if (io->use_tensor_cores != 2) {
@@ -728,22 +861,34 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             SPB_LAUNCH_CHECK();
             prof_end(s);
         }
-        // 5x5 layer(s) on the new h
-        prof_begin(kTagConvP, s);
-        {
-            ConvGemmArgs a{ws.h_hi[nxt], ws.h_lo[nxt], (const __half *)w->wp_hi, (const __half *)w->wp_lo, io->d_w_row_base,
-                           (int64_t)w->n_weight_sets * kE, w->bias_p, ws.feat, (int64_t)HD * kE, (int)N, HD * kE, 5,
-                           w->inv_scale_p};
-            SPB_TRY(conv_gemm(a, tc, s));
+        if (tc) {
+            // composed head straight from h: stop / action maps + duration windows (no 5x5 GEMM)
+            prof_begin(kTagHead, s);
+            SPB_CUDA(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 25 * kE * 2 * 4));
+            head_maps_kernel<<<dim3(kHW / 120, (unsigned)(N * HD)), 256, 25 * kE * 2 * 4, s>>>(
+                ws.h_hi[nxt], ws.h_lo[nxt], w->w23_eff, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3);
+            SPB_LAUNCH_CHECK();
+            head_drt_kernel<<<(unsigned)((N * HD * 48 * 32 + 255) / 256), 256, 0, s>>>(
+                ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff, io->d_w_row_base, HD, ws.drt_pre, N);
+            SPB_LAUNCH_CHECK();
+        } else {
+            // verification path: the explicit 5x5 layer(s), then the three head convolutions on feat
+            prof_begin(kTagConvP, s);
+            {
+                ConvGemmArgs a{ws.h_hi[nxt], ws.h_lo[nxt], (const __half *)w->wp_hi, (const __half *)w->wp_lo,
+                               io->d_w_row_base, (int64_t)w->n_weight_sets * kE, w->bias_p, ws.feat, (int64_t)HD * kE,
+                               (int)N, HD * kE, 5, w->inv_scale_p};
+                SPB_TRY(conv_gemm(a, false, s));
+            }
+            prof_end(s);
+            prof_begin(kTagHead, s);
+            head_reduce_kernel<<<(unsigned)((N * HD * kHW * 32 + 255) / 256), 256, 0, s>>>(ws.feat, HD, w->w2, w->w3,
+                                                                                          w->wd1, ws.y2, ws.y3, ws.dc, N);
+            SPB_LAUNCH_CHECK();
         }
-        prof_end(s);
-        prof_begin(kTagHead, s);
-        head_reduce_kernel<<<(unsigned)((N * HD * kHW * 32 + 255) / 256), 256, 0, s>>>(ws.feat, HD, w->w2, w->w3, w->wd1,
-                                                                                      ws.y2, ws.y3, ws.dc, N);
-        SPB_LAUNCH_CHECK();
-        head_finish_kernel<<<(unsigned)(N * HD), 256, 0, s>>>(ws.y2, ws.y3, ws.dc, w->wd2, *w, ws.vfmean, ws.sp_feat,
-                                                              io->d_probs, io->d_mu, io->d_sigma2, io->d_action_map, HD,
-                                                              N, t, T);
+        head_finish_kernel<<<(unsigned)(N * HD), 256, 0, s>>>(ws.y2, ws.y3, ws.dc, tc ? ws.drt_pre : nullptr, w->wd2, *w,
+                                                              ws.vfmean, ws.sp_feat, io->d_probs, io->d_mu, io->d_sigma2,
+                                                              io->d_action_map, HD, N, t, T);
         SPB_LAUNCH_CHECK();
         prof_end(s);
         if (t + 1 < T) {

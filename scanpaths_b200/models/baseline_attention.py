@@ -98,6 +98,36 @@ def prepare_weights(sd, task: str, device):
     t["b_spatial_embed"] = f("spatial_embed.bias").contiguous()
     t["w_semantic_embed"] = f("semantic_embed.weight").contiguous()
     t["b_semantic_embed"] = f("semantic_embed.bias").contiguous()
+    # composed head: feat = conv5x5(h) + bp is consumed only by linear maps (sal_layer_2, sal_layer_3 1x1,
+    # drt_layer_1 7x7 stride 5) before any nonlinearity (predict_head.forward :144-150), so
+    #   y2/y3[p] = sum_{tap,ci} (sum_c w[c] Wp[c,ci,tap]) h[ci,p+tap] + (w.bp + b)
+    #   drt[oy,ox] = sum_{ci,11x11} (wd (*) Wp)[ci,dy,dx] h[ci,5oy-4+dy,5ox-4+dx] + const, where drt taps that
+    #   land on the zero padding of feat (top row / left column windows) are masked out -> 4 variants.
+    # Composed in float64, stored float32.
+    wp64 = torch.stack([f(s_ + ".weight").double() for s_ in sets], 0)           # [sets, c, ci, 5, 5]
+    bp64 = torch.stack([f(s_ + ".bias").double() for s_ in sets], 0)             # [sets, c]
+    w2_64 = f("object_head.sal_layer_2.weight").double().reshape(512)
+    w3_64 = f("object_head.sal_layer_3.weight").double().reshape(512)
+    wd_64 = f("object_head.drt_layer_1.weight").double()[0]                      # [c, 7, 7]
+    w23 = torch.stack([torch.einsum("c,scikl->skli", w2_64, wp64), torch.einsum("c,scikl->skli", w3_64, wp64)], -1)
+    t["w23_eff"] = w23.reshape(len(sets), 25, 512, 2).float().contiguous()
+    b23 = torch.stack([bp64 @ w2_64 + f("object_head.sal_layer_2.bias").double()[0],
+                       bp64 @ w3_64 + f("object_head.sal_layer_3.bias").double()[0]], -1)
+    t["b23_eff"] = b23.float().contiguous()
+    wde, bde = [], []
+    for top in (0, 1):
+        for left in (0, 1):
+            m = wd_64.clone()
+            if top:
+                m[:, :2, :] = 0
+            if left:
+                m[:, :, :2] = 0
+            # full 2-D convolution of the masked 7x7 with each 5x5, summed over c -> [sets, ci, 11, 11]
+            comp = torch.stack([F.conv_transpose2d(m[None], wp64[i])[0] for i in range(len(sets))], 0)
+            wde.append(comp.permute(0, 2, 3, 1).reshape(len(sets), 121, 512))
+            bde.append(bp64 @ m.sum(dim=(1, 2)) + f("object_head.drt_layer_1.bias").double()[0])
+    t["wd_eff"] = torch.stack(wde, 1).float().contiguous()                       # [sets, 4, 121, 512]
+    t["bd_eff"] = torch.stack(bde, 1).float().contiguous()                       # [sets, 4]
     # spatial_att: score_j = <spatial_attention, conv3x3(spatial_lists, list_j)> + const
     #            = <w_eff, list_j> + const  (adjoint of the 3x3 correlation applied to spatial_attention)
     watt = f("spatial_att.spatial_attention.weight").double().view(1, 1, 30, 40)
