@@ -400,72 +400,113 @@ __device__ __forceinline__ void load_h4(const __half *hi, const __half *lo, int6
     v[2] = fa1.x + fb1.x * (1.0f / kLoScale); v[3] = fa1.y + fb1.y * (1.0f / kLoScale);
 }
 
-// y2[p], y3[p] for a 3-row pixel tile of one (image, head); weights of the image's set in shared
-// memory ([25][512][2] fp32 = 100 KB); each warp walks its 15 pixels in groups of 3 so that one
-// weight fetch serves three pixels; lane owns channels lane*4 + 128*j.
-constexpr int kMapsPix = 3;
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void load_h8(const __half *hi, const __half *lo, int64_t off, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(hi + off), b = *reinterpret_cast<const uint4 *>(lo + off);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[i]));
+        const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[i]));
+        v[2 * i] = fa.x + fb.x * (1.0f / kLoScale);
+        v[2 * i + 1] = fa.y + fb.y * (1.0f / kLoScale);
+    }
+}
+
+// y2[p], y3[p] for a 3-row pixel tile of one (image, head): a register-tiled direct convolution.
+// Per 64-channel chunk the 7 x 44 halo of h (fp32, rebuilt from the hi/lo pair, zero outside the
+// image) and the chunk's weights [25][64][2] are staged in shared memory; lane l owns channels
+// (2l, 2l+1) of the chunk, a warp owns 8-pixel row segments, and per filter row a lane loads 12
+// h pairs + 5 weight quads for 160 FMAs.  Channel partial sums stay in registers across all 8
+// chunks and are reduced across the warp once.  ~1.6 GB of L2 traffic per 256-image step instead
+// of 15.7 GB for the naive gather; FMA-bound.
+constexpr int kMapsChunk = 64, kHaloH = 7, kHaloW = 44;
+constexpr int kMapsSmemBytes = (kHaloH * kHaloW * kMapsChunk + 25 * kMapsChunk * 2) * 4;   // 91,648 B
+__global__ void __launch_bounds__(256, 2)
 head_maps_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ w23,
                  const float *__restrict__ b23, const int32_t *__restrict__ w_row_base, int HD,
                  float *__restrict__ y2, float *__restrict__ y3) {
-    extern __shared__ float wsm[];                    // [25][512][2]
+    extern __shared__ float sm[];
+    float *hs = sm;                                          // [7][44][64]
+    float *ws = sm + kHaloH * kHaloW * kMapsChunk;           // [25][64][2]
     const int64_t nh = blockIdx.y;
     const int64_t n = nh / HD;
     const int hd = (int)(nh % HD);
     const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
-    const float4 *src = reinterpret_cast<const float4 *>(w23 + (int64_t)set * 25 * kE * 2);
-    for (int i = threadIdx.x; i < 25 * kE * 2 / 4; i += blockDim.x) reinterpret_cast<float4 *>(wsm)[i] = src[i];
-    __syncthreads();
+    const int y0 = blockIdx.x * 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p_first = blockIdx.x * 120 + warp * 15;
-    const float bias2 = b23[set * 2], bias3 = b23[set * 2 + 1];
-    for (int g = 0; g < 15; g += kMapsPix) {
-        float a2[kMapsPix], a3[kMapsPix];
-        int py[kMapsPix], px[kMapsPix];
+    const float *wset = w23 + (int64_t)set * 25 * kE * 2;
+    float acc[2][8][2];
 #pragma unroll
-        for (int u = 0; u < kMapsPix; ++u) {
-            a2[u] = 0.0f; a3[u] = 0.0f;
-            const int p = p_first + g + u;
-            py[u] = p / kW; px[u] = p - py[u] * kW;
+    for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[sg][i][0] = 0.0f; acc[sg][i][1] = 0.0f; }
+
+    for (int chunk = 0; chunk < kE / kMapsChunk; ++chunk) {
+        __syncthreads();                                     // previous chunk fully consumed
+        // ---- stage the halo: item = (halo pixel, 8-channel group)
+        for (int it = threadIdx.x; it < kHaloH * kHaloW * (kMapsChunk / 8); it += 256) {
+            const int grp = it & 7, hp = it >> 3;
+            const int hy = hp / kHaloW, hx = hp - hy * kHaloW;
+            const int yy = y0 - 2 + hy, xx = hx - 2;
+            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (yy >= 0 && yy < kH && xx >= 0 && xx < kW)
+                load_h8(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + chunk * kMapsChunk + grp * 8, v);
+            float4 *dst = reinterpret_cast<float4 *>(hs + hp * kMapsChunk + grp * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
-        for (int tap = 0; tap < 25; ++tap) {
-            const int dy = tap / 5 - 2, dx = tap % 5 - 2;
-            float w[4][8];
+        for (int it = threadIdx.x; it < 25 * kMapsChunk * 2 / 4; it += 256) {
+            const int tap = it / (kMapsChunk * 2 / 4), r4 = it - tap * (kMapsChunk * 2 / 4);
+            reinterpret_cast<float4 *>(ws)[it] =
+                *reinterpret_cast<const float4 *>(wset + ((int64_t)tap * kE + chunk * kMapsChunk) * 2 + r4 * 4);
+        }
+        __syncthreads();
+        // ---- compute: warp w owns segments w and w + 8 (15 segments of 8 pixels)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 *wp = reinterpret_cast<const float4 *>(wsm + (tap * kE + lane * 4 + 128 * j) * 2);
-                const float4 w0 = wp[0], w1 = wp[1];
-                w[j][0] = w0.x; w[j][1] = w0.y; w[j][2] = w0.z; w[j][3] = w0.w;
-                w[j][4] = w1.x; w[j][5] = w1.y; w[j][6] = w1.z; w[j][7] = w1.w;
-            }
+        for (int sg = 0; sg < 2; ++sg) {
+            const int seg = warp + 8 * sg;
+            if (seg < 15) {
+                const int row = seg / 5, x0 = (seg % 5) * 8;
+#pragma unroll 1
+                for (int ky = 0; ky < 5; ++ky) {
+                    float2 hr[12];
+                    const float *hp = hs + ((row + ky) * kHaloW + x0) * kMapsChunk + 2 * lane;
 #pragma unroll
-            for (int u = 0; u < kMapsPix; ++u) {
-                const int yy = py[u] + dy, xx = px[u] + dx;
-                if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;     // zero padding of the 5x5 layer
-                const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 4;
+                    for (int i = 0; i < 12; ++i) hr[i] = *reinterpret_cast<const float2 *>(hp + i * kMapsChunk);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float hv[4];
-                    load_h4(h_hi, h_lo, base + 128 * j, hv);
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(ws + ((ky * 5 + kx) * kMapsChunk + 2 * lane) * 2);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a2[u] = fmaf(hv[e], w[j][2 * e], a2[u]);
-                        a3[u] = fmaf(hv[e], w[j][2 * e + 1], a3[u]);
+                        for (int px = 0; px < 8; ++px) {
+                            const float2 hv = hr[px + kx];
+                            acc[sg][px][0] = fmaf(hv.x, w4.x, acc[sg][px][0]);
+                            acc[sg][px][1] = fmaf(hv.x, w4.y, acc[sg][px][1]);
+                            acc[sg][px][0] = fmaf(hv.y, w4.z, acc[sg][px][0]);
+                            acc[sg][px][1] = fmaf(hv.y, w4.w, acc[sg][px][1]);
+                        }
                     }
                 }
             }
         }
+    }
+    const float bias2 = b23[set * 2], bias3 = b23[set * 2 + 1];
 #pragma unroll
-        for (int u = 0; u < kMapsPix; ++u) {
-            float s2 = a2[u], s3 = a3[u];
-            for (int o = 16; o > 0; o >>= 1) {
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-            }
-            if (lane == 0) {
-                const int64_t o = nh * kHW + p_first + g + u;
-                y2[o] = s2 + bias2;      // head_finish adds nothing more: b2 / b3 are folded into b23_eff
-                y3[o] = s3 + bias3;
+    for (int sg = 0; sg < 2; ++sg) {
+        const int seg = warp + 8 * sg;
+        if (seg < 15) {                                      // warp-uniform
+            const int row = seg / 5, x0 = (seg % 5) * 8;
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+                float s2 = acc[sg][px][0], s3 = acc[sg][px][1];
+                for (int o = 16; o > 0; o >>= 1) {
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                }
+                if (lane == 0) {
+                    const int64_t o = nh * kHW + (y0 + row) * kW + x0 + px;
+                    y2[o] = s2 + bias2;      // b2 / b3 are folded into b23_eff
+                    y3[o] = s3 + bias3;
+                }
             }
         }
     }
@@ -491,14 +532,17 @@ head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo
     for (int tap = 0; tap < 121; ++tap) {
         const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
         if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
-        const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 4;
+        const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float hv[4];
-            load_h4(h_hi, h_lo, base + 128 * j, hv);
-            const float4 w4 = *reinterpret_cast<const float4 *>(wv + tap * kE + lane * 4 + 128 * j);
-            acc = fmaf(hv[0], w4.x, acc); acc = fmaf(hv[1], w4.y, acc);
-            acc = fmaf(hv[2], w4.z, acc); acc = fmaf(hv[3], w4.w, acc);
+        for (int j = 0; j < 2; ++j) {
+            float hv[8];
+            load_h8(h_hi, h_lo, base + 256 * j, hv);
+            const float4 *wq = reinterpret_cast<const float4 *>(wv + tap * kE + lane * 8 + 256 * j);
+            const float4 w0 = wq[0], w1 = wq[1];
+            acc = fmaf(hv[0], w0.x, acc); acc = fmaf(hv[1], w0.y, acc);
+            acc = fmaf(hv[2], w0.z, acc); acc = fmaf(hv[3], w0.w, acc);
+            acc = fmaf(hv[4], w1.x, acc); acc = fmaf(hv[5], w1.y, acc);
+            acc = fmaf(hv[6], w1.z, acc); acc = fmaf(hv[7], w1.w, acc);
         }
     }
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
@@ -864,8 +908,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         if (tc) {
             // composed head straight from h: stop / action maps + duration windows (no 5x5 GEMM)
             prof_begin(kTagHead, s);
-            SPB_CUDA(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 25 * kE * 2 * 4));
-            head_maps_kernel<<<dim3(kHW / 120, (unsigned)(N * HD)), 256, 25 * kE * 2 * 4, s>>>(
+            SPB_CUDA(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMapsSmemBytes));
+            head_maps_kernel<<<dim3(kHW / 120, (unsigned)(N * HD)), 256, kMapsSmemBytes, s>>>(
                 ws.h_hi[nxt], ws.h_lo[nxt], w->w23_eff, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3);
             SPB_LAUNCH_CHECK();
             head_drt_kernel<<<(unsigned)((N * HD * 48 * 32 + 255) / 256), 256, 0, s>>>(
