@@ -872,16 +872,12 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
                              ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
         prof_end(s);
-        // 3x3 gate convolutions of h + ConvLSTM cell (fused into the GEMM epilogue on the tensor-core path)
+        // 3x3 gate convolutions of h, then the ConvLSTM cell
         const int cur = t & 1, nxt = cur ^ 1;
         prof_begin(kTagConvH, s);
         {
             ConvGemmArgs a{ws.h_hi[cur], ws.h_lo[cur], (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr,
                            kGateCols, nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
-            if (io->use_tensor_cores == 2) {   // experimental: cell fused into the GEMM epilogue (slower)
-                a.mode = 1; a.xg = ws.xg; a.c = ws.c; a.V = ws.V; a.sp_mem = ws.sp_mem; a.n_streams = S;
-                a.h_out_hi = ws.h_hi[nxt]; a.h_out_lo = ws.h_lo[nxt];
-            }
             if (t == 0 && a.mode == 0) {
                 SPB_CUDA(cudaMemsetAsync(ws.acc, 0, NP * kGateCols * 4, s));   // h(0) = 0: its convolution is exactly 0
             } else {
@@ -889,7 +885,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             }
         }
         prof_end(s);
-        if (io->use_tensor_cores != 2) {
+        {
             prof_begin(kTagCell, s);
             if (tc) {
                 if (S == 1)

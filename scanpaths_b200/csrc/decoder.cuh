@@ -25,21 +25,11 @@ struct ConvGemmArgs {
     int64_t ldo;
     int n_images, cols, ks;
     float inv_scale;
-    // mode 1 (tensor-core path only): the ConvLSTM cell is fused into the epilogue of the 3x3 gate
-    // convolution -- gates = out + xg + rank-1 memory term; c' = f c + i g; h' = o c' is written
-    // as the fp16 pair the next convolutions consume.  `out` is unused in this mode.
-    int mode = 0;
-    const float *xg = nullptr;        // [N,1200,2048] x-convolution + biases, same column order as the weights
-    float *c = nullptr;               // [N,1200,512] cell state, updated in place
-    const float *V = nullptr;         // [N,S,3,512,9] rank-1 projections
-    const float *sp_mem = nullptr;    // [N,S,1200] spatial memory
-    int n_streams = 0;
-    __half *h_out_hi = nullptr, *h_out_lo = nullptr;   // [N,1200,512] next hidden state (NOT the buffer being read)
+    int mode = 0;                     // reserved (0)
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].
-// One epilogue thread of the tensor-core kernel owns one pixel x one (cb, half): all four gates of
-// 32 channels sit in its 128 accumulator columns.
+// (a 128-row weight tile of the tensor-core kernel = all four gates of 32 channels.)
 __host__ __device__ inline int gate_col(int ch, int g) {
     return (ch >> 6) * 256 + ((ch >> 5) & 1) * 128 + g * 32 + (ch & 31);
 }

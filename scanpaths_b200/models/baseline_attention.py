@@ -158,7 +158,7 @@ class CudaDecoder:
         self.lib = _lib.load()
         self.task, self.steps, self.wave = task, int(steps), int(wave)
         self.device = torch.device(device)
-        self.use_tensor_cores = int(use_tensor_cores)     # 0 SIMT check path, 1 tcgen05, 2 tcgen05 + fused cell (experimental)
+        self.use_tensor_cores = int(use_tensor_cores)     # 0 = SIMT check path (explicit 5x5 layer), 1 = tcgen05 + composed head
         self.tensors, self.w = prepare_weights(state_dict, task, self.device)
         self.heads = int(self.w.n_heads)
         self._ws, self._ws_n = None, 0

@@ -67,7 +67,7 @@ def test_conv_gemm_simt_vs_torch_fp64(lib, ks, cols):
     assert err < 1e-5 * mag, (err, mag)      # plain sequential fp32 accumulation over K = ks*ks*512
 
 
-@pytest.mark.parametrize("ks,cols,sets", [(3, 256, 0), (3, 2048, 0), (5, 512, 0), (5, 512, 3)])
+@pytest.mark.parametrize("ks,cols,sets", [(3, 128, 0), (3, 2048, 0), (5, 512, 0), (5, 512, 3)])
 def test_conv_gemm_tensor_core_vs_torch_fp64(lib, ks, cols, sets):
     err, mag = _conv_case(lib, ks, 3, cols, use_tc=True, per_image_sets=sets)
     print("tcgen05 conv ks=%d cols=%d max abs err %.3e (max |out| %.2f)" % (ks, cols, err, mag))
@@ -108,12 +108,12 @@ def _decode_case(name, use_tc, golden_dir, steps=None):
 
 
 @pytest.mark.parametrize("name", ["coco", "air", "osie"])
-@pytest.mark.parametrize("use_tc", [0, 1, 2])
+@pytest.mark.parametrize("use_tc", [0, 1])
 def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
-    """use_tc: 0 = SIMT fp32 check kernels, 1 = tcgen05 (product path), 2 = tcgen05 with the ConvLSTM
-    cell fused into the GEMM epilogue (experimental variant, kept verified)."""
+    """use_tc: 0 = SIMT fp32 check kernels with the explicit 5x5 layer (an independent route to the
+    same numbers), 1 = the product path (tcgen05 gate GEMM + composed head)."""
     worst = _decode_case(name, use_tc, golden_dir)
-    print(name, ["simt", "tc", "tc-fused"][use_tc], worst)
+    print(name, ["simt", "tc"][use_tc], worst)
     for k, v in worst.items():
         if k.endswith("ref_f32_prob"):
             continue
