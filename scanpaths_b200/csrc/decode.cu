@@ -512,16 +512,17 @@ head_maps_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_l
     }
 }
 
-// duration pre-activation of the 48 windows: one warp per (image, head, window).
-__global__ void __launch_bounds__(256)
+// duration pre-activation of the 48 windows: one 4-warp block per (image, head, window); the 121
+// taps are dealt round-robin to the warps, lanes split the channels, partial sums meet in smem.
+__global__ void __launch_bounds__(128)
 head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ wd_eff,
                 const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD,
-                float *__restrict__ drt_pre, int64_t n_images) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (warp >= n_images * HD * 48) return;
-    const int o = (int)(warp % 48);
-    const int64_t nh = warp / 48;
+                float *__restrict__ drt_pre) {
+    __shared__ float part[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t win = blockIdx.x;                   // (n*HD + hd)*48 + o
+    const int o = (int)(win % 48);
+    const int64_t nh = win / 48;
     const int64_t n = nh / HD;
     const int hd = (int)(nh % HD);
     const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
@@ -529,7 +530,7 @@ head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo
     const int variant = 2 * (oy == 0) + (ox == 0);
     const float *wv = wd_eff + ((int64_t)set * 4 + variant) * 121 * kE;
     float acc = 0.0f;
-    for (int tap = 0; tap < 121; ++tap) {
+    for (int tap = warp; tap < 121; tap += 4) {
         const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
         if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
         const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
@@ -546,7 +547,9 @@ head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo
         }
     }
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) drt_pre[warp] = acc + bd_eff[set * 4 + variant];
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) drt_pre[win] = ((part[0] + part[1]) + (part[2] + part[3])) + bd_eff[set * 4 + variant];
 }
 
 __device__ __forceinline__ float block_reduce(float v, float *sh, bool is_max) {
@@ -647,12 +650,16 @@ semantic_feat_kernel(const float *__restrict__ vf, const float *__restrict__ map
     if (warp >= n_images * kE) return;
     const int64_t n = warp / kE;
     const int c = (int)(warp - n * kE);
-    const float *row = vf + (n * kE + c) * kHW;
+    const float4 *row = reinterpret_cast<const float4 *>(vf + (n * kE + c) * kHW);
     float s[2] = {0.0f, 0.0f};
-    for (int p = lane; p < kHW; p += 32) {
-        const float v = row[p];
-        for (int st = 0; st < S; ++st)
-            s[st] = fmaf(v, maps ? maps[n * image_stride + st * stream_stride + p] : 0.0f, s[st]);
+    for (int p4 = lane; p4 < kHW / 4; p4 += 32) {
+        const float4 v = row[p4];
+        for (int st = 0; st < S; ++st) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (maps) m = *reinterpret_cast<const float4 *>(maps + n * image_stride + st * stream_stride + 4 * p4);
+            s[st] = fmaf(v.x, m.x, s[st]); s[st] = fmaf(v.y, m.y, s[st]);
+            s[st] = fmaf(v.z, m.z, s[st]); s[st] = fmaf(v.w, m.w, s[st]);
+        }
     }
     for (int st = 0; st < S; ++st) {
         float a = s[st];
@@ -908,8 +915,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             head_maps_kernel<<<dim3(kHW / 120, (unsigned)(N * HD)), 256, kMapsSmemBytes, s>>>(
                 ws.h_hi[nxt], ws.h_lo[nxt], w->w23_eff, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3);
             SPB_LAUNCH_CHECK();
-            head_drt_kernel<<<(unsigned)((N * HD * 48 * 32 + 255) / 256), 256, 0, s>>>(
-                ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff, io->d_w_row_base, HD, ws.drt_pre, N);
+            head_drt_kernel<<<(unsigned)(N * HD * 48), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
+                                                                   io->d_w_row_base, HD, ws.drt_pre);
             SPB_LAUNCH_CHECK();
         } else {
             // verification path: the explicit 5x5 layer(s), then the three head convolutions on feat
