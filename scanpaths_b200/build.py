@@ -40,6 +40,7 @@ def build_library(force: bool = False, verbose: bool = False):
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("SPB_NVCC_EXTRA", "").split()      # e.g. -DSPB_TC_BLOCKK=32 -DSPB_TC_STAGES=4
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")

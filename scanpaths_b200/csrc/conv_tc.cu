@@ -38,7 +38,15 @@ namespace spb {
 
 namespace tc {
 
-constexpr int kTileCh = 128, kTilePix = 240, kBlockK = 64, kStages = 2;
+#ifndef SPB_TC_BLOCKK
+#define SPB_TC_BLOCKK 64
+#endif
+#ifndef SPB_TC_STAGES
+#define SPB_TC_STAGES 2
+#endif
+constexpr int kTileCh = 128, kTilePix = 240, kBlockK = SPB_TC_BLOCKK, kStages = SPB_TC_STAGES;
+constexpr int kSwizzleBytes = kBlockK * 2;                // one K-block row: 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
+static_assert(kSwizzleBytes == 128 || kSwizzleBytes == 64, "BLOCK_K must be 64 or 32 fp16 elements");
 constexpr int kWBytes = kTileCh * kBlockK * 2;            // 16 KB per weight operand tile
 constexpr int kActBytes = kTilePix * kBlockK * 2;         // 30 KB per activation operand tile
 constexpr int kStageBytes = 2 * kWBytes + 2 * kActBytes;  // 92 KB: W_hi, W_lo, A_hi, A_lo
@@ -91,9 +99,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * kSwizzleBytes) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(kSwizzleBytes == 128 ? 2 : 4) << 61;
     return d;
 }
 
@@ -334,7 +342,7 @@ static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images) {
     const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kW, (cuuint32_t)(kTilePix / kW), 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, kSwizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -345,7 +353,7 @@ static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K
     const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileCh};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, kSwizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }

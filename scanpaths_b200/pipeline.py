@@ -41,6 +41,11 @@ class ScanpathPipeline:
         self._ws = S.Workspace(int(self.humans.nwd.max().item()), self.device)
         return self.humans
 
+    def _copy_stream(self):
+        if getattr(self, "_cs", None) is None:
+            self._cs = torch.cuda.Stream(device=self.device)
+        return self._cs
+
     def _pair_map(self, n, n0):
         key = (n, n0)
         if key not in self._pairs:
@@ -64,12 +69,30 @@ class ScanpathPipeline:
         acc = torch.zeros((HD, 12), dtype=torch.float64, device=dev)   # sum, sumsq (4 each), best sums/sumsq (2+2)
         paths = [] if keep_paths else None
         host_in = not visual_feature.is_cuda
-        for n0 in range(0, N, self.wave):
+        # host input: the next wave's features are copied on a side stream while this wave computes
+        copy_stream = self._copy_stream() if host_in else None
+        main = torch.cuda.current_stream(dev)
+        starts = list(range(0, N, self.wave))
+
+        def fetch(n0):
+            n1 = min(N, n0 + self.wave)
+            with torch.cuda.stream(copy_stream):
+                t = visual_feature[n0:n1].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
+
+        pending = fetch(starts[0]) if host_in else None
+        for wi, n0 in enumerate(starts):
             n1 = min(N, n0 + self.wave)
             n = n1 - n0
-            vf = visual_feature[n0:n1]
             if host_in:
-                vf = vf.to(dev, non_blocking=True)
+                vf, ev = pending
+                main.wait_event(ev)
+                vf.record_stream(main)
+                pending = fetch(starts[wi + 1]) if wi + 1 < len(starts) else None
+            else:
+                vf = visual_feature[n0:n1]
             att = None if attention_maps is None else attention_maps[n0:n1].to(dev, non_blocking=True)
             tk = None if tasks is None else tasks[n0:n1]
             probs, mu, s2, _ = self.decoder.decode(vf, att, tk)
