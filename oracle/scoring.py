@@ -265,12 +265,15 @@ def evaluation(gt_fix_vectors, predict_fix_vectors):
     return m, s, per_image
 
 
-def human_evaluation(batches_fix_vectors):
+def human_evaluation(batches_fix_vectors, per_image_best=False):
     """OSIE/utils/evaluation.py:11-148 minus MultiMatch: ordered pairs (i, j!=i)
     inside each image; first scanpath plays 'human', second 'simulated'.
-    `batches_fix_vectors`: list over images of list over subjects."""
+    `batches_fix_vectors`: list over images of list over subjects.
+    per_image_best=True is the COCO-Search18 variant (COCO_Search18/utils/evaluation.py:88-125):
+    the number of subjects may differ per image and SED_best / STDE_best are the min / max over
+    ALL ordered pairs of an image (OSIE: per first subject, with a constant subject count)."""
     sm_wd, sm_wod = eval_scanmatch_objects()
-    wd, wod, sed, stde, per_image = [], [], [], [], []
+    wd, wod, sed, stde, per_image, best = [], [], [], [], [], []
     last_S = 0
     for fvs in batches_fix_vectors:
         arrs = [structured_to_array(f) for f in fvs]
@@ -282,16 +285,19 @@ def human_evaluation(batches_fix_vectors):
                 r = score_pair(arrs[i], arrs[j], sm_wd, sm_wod)
                 wd.append(r[0]); wod.append(r[1]); sed.append(r[2]); stde.append(r[3])
                 rows.append(r)
-        per_image.append(list(np.array(rows, dtype=np.float64).mean(axis=0)))
+        rows = np.array(rows, dtype=np.float64)
+        per_image.append(list(rows.mean(axis=0)))
+        best.append((rows[:, 2].min(), rows[:, 3].max()))
         last_S = len(fvs)
-    sed_t = np.array(sed).reshape(-1, last_S - 1)
-    stde_t = np.array(stde).reshape(-1, last_S - 1)
+    if per_image_best:
+        sed_best, stde_best = np.array([b[0] for b in best]), np.array([b[1] for b in best])
+    else:
+        sed_best = np.array(sed).reshape(-1, last_S - 1).min(-1)
+        stde_best = np.array(stde).reshape(-1, last_S - 1).max(-1)
     m = {"ScanMatch": {"w/o duration": np.mean(wod), "with duration": np.mean(wd)},
-         "VAME": {"SED": sed_t.mean(), "STDE": stde_t.mean(),
-                  "SED_best": sed_t.min(-1).mean(), "STDE_best": stde_t.max(-1).mean()}}
+         "VAME": {"SED": np.mean(sed), "STDE": np.mean(stde), "SED_best": sed_best.mean(), "STDE_best": stde_best.mean()}}
     s = {"ScanMatch": {"w/o duration": np.std(wod), "with duration": np.std(wd)},
-         "VAME": {"SED": sed_t.std(), "STDE": stde_t.std(),
-                  "SED_best": sed_t.min(-1).std(), "STDE_best": stde_t.max(-1).std()}}
+         "VAME": {"SED": np.std(sed), "STDE": np.std(stde), "SED_best": sed_best.std(), "STDE_best": stde_best.std()}}
     return m, s, per_image
 
 

@@ -98,9 +98,11 @@ def evaluation(gt_fix_vectors, predict_fix_vectors, is_eliminating_nan=True):
     return m, s, _per_group_means(scores, sizes)
 
 
-def human_evaluation(dataloader):
+def human_evaluation(dataloader, per_image_best=False):
     """OSIE/utils/evaluation.py:11-148: all ordered pairs (i, j != i) of each image's
-    subjects; i plays the human, j the simulated scanpath."""
+    subjects; i plays the human, j the simulated scanpath.  per_image_best=True is the
+    COCO-Search18 variant (COCO_Search18/utils/evaluation.py:88-125): subject counts may differ per
+    image and SED_best / STDE_best are taken over all ordered pairs of an image."""
     cfg = _eval_cfg()
     paths, pair_h, pair_s, sizes, names = [], [], [], [], []
     last_S = 0
@@ -119,9 +121,22 @@ def human_evaluation(dataloader):
     dev = cfg.device
     scores = S.score_pairs(pack, pack, torch.tensor(pair_h, dtype=torch.int32, device=dev),
                            torch.tensor(pair_s, dtype=torch.int32, device=dev), cfg)
-    m, s = _metric_dicts(scores, last_S - 1)
+    if per_image_best:
+        sc = scores.cpu().numpy()
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        sed_b = np.array([sc[off[i]:off[i + 1], 2].min() for i in range(len(sizes))])
+        stde_b = np.array([sc[off[i]:off[i + 1], 3].max() for i in range(len(sizes))])
+        m = {"MultiMatch": _nan5(),
+             "ScanMatch": {"w/o duration": sc[:, 1].mean(), "with duration": sc[:, 0].mean()},
+             "VAME": {"SED": sc[:, 2].mean(), "STDE": sc[:, 3].mean(), "SED_best": sed_b.mean(),
+                      "STDE_best": stde_b.mean()}}
+        s = {"MultiMatch": _nan5(),
+             "ScanMatch": {"w/o duration": sc[:, 1].std(), "with duration": sc[:, 0].std()},
+             "VAME": {"SED": sc[:, 2].std(), "STDE": sc[:, 3].std(), "SED_best": sed_b.std(), "STDE_best": stde_b.std()}}
+    else:
+        m, s = _metric_dicts(scores, last_S - 1)
     per = _per_group_means(scores, sizes)
-    return m, s, {name: sc for name, sc in zip(names, per)}
+    return m, s, {name: sc_ for name, sc_ in zip(names, per)}
 
 
 def pairs_eval(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None, ScanMatchwithoutDuration=None,

@@ -204,6 +204,18 @@ def gen_eval():
         pe.append(ns.evaluation.pairs_eval_scanmatch(gt_struct, [to_struct(preds[i][k]) for i in range(N)],
                                                      wd_obj, wod_obj))
     out["pairs_eval_scanmatch"] = np.array(pe, dtype=np.float64)  # [K, N, 2]
+    # COCO human_evaluation: variable number of subjects per image, per-image best (:88-125)
+    sizes = [3, 5, 2, 4, 5, 3]
+    ragged = [gt_struct[i][:sizes[i]] for i in range(N)]
+    loader = Loader([{"fix_vectors": ragged[:4], "img_names": ["a", "b", "c", "d"]},
+                     {"fix_vectors": ragged[4:], "img_names": ["e", "f"]}])
+    m, s, per = ns.evaluation.human_evaluation(loader)
+    out["coco_human_sizes"] = np.array(sizes)
+    out["coco_human_mean"] = np.array([m["ScanMatch"]["w/o duration"], m["ScanMatch"]["with duration"],
+                                       m["VAME"]["SED"], m["VAME"]["STDE"], m["VAME"]["SED_best"], m["VAME"]["STDE_best"]])
+    out["coco_human_std"] = np.array([s["ScanMatch"]["w/o duration"], s["ScanMatch"]["with duration"],
+                                      s["VAME"]["SED"], s["VAME"]["STDE"], s["VAME"]["SED_best"], s["VAME"]["STDE_best"]])
+    out["coco_human_per_image"] = np.array([per[k] for k in "abcdef"], dtype=np.float64)[:, 5:]
     np.savez_compressed(os.path.join(HERE, "eval_drivers.npz"), **out)
     print("eval goldens written")
 

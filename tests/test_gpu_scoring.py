@@ -184,6 +184,13 @@ def test_mirror_evaluation_drivers(S, golden_dir):
     np.testing.assert_allclose(_flat(m), g["human_mean"], rtol=1e-12)
     np.testing.assert_allclose(_flat(s), g["human_std"], rtol=1e-10)
     np.testing.assert_allclose(np.array([per[k] for k in "abcdef"])[:, 5:], g["human_per_image"], rtol=1e-12)
+    ragged = [humans[i][:int(g["coco_human_sizes"][i])] for i in range(N)]
+    loader = [{"fix_vectors": ragged[:4], "img_names": ["a", "b", "c", "d"]},
+              {"fix_vectors": ragged[4:], "img_names": ["e", "f"]}]
+    m, s, per = E.human_evaluation(loader, per_image_best=True)          # COCO-Search18 variant
+    np.testing.assert_allclose(_flat(m), g["coco_human_mean"], rtol=1e-12)
+    np.testing.assert_allclose(_flat(s), g["coco_human_std"], rtol=1e-10)
+    np.testing.assert_allclose(np.array([per[k] for k in "abcdef"])[:, 5:], g["coco_human_per_image"], rtol=1e-12)
     for k in range(K):
         pe = E.pairs_eval(humans, [preds[i][k] for i in range(N)], None, None)
         np.testing.assert_allclose(pe[:, 5:], g["pairs_eval"][k][:, 5:], rtol=1e-6, equal_nan=True)

@@ -100,6 +100,11 @@ def test_eval_drivers(golden_dir):
     np.testing.assert_allclose(_flat(m), g["human_mean"], rtol=1e-13)
     np.testing.assert_allclose(_flat(s), g["human_std"], rtol=1e-12)
     np.testing.assert_allclose(np.array(per), g["human_per_image"], rtol=1e-13)
+    ragged = [humans[i][:int(g["coco_human_sizes"][i])] for i in range(N)]
+    m, s, per = O.human_evaluation(ragged, per_image_best=True)
+    np.testing.assert_allclose(_flat(m), g["coco_human_mean"], rtol=1e-13)
+    np.testing.assert_allclose(_flat(s), g["coco_human_std"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(per), g["coco_human_per_image"], rtol=1e-13)
     for k in range(K):
         pe = O.pairs_eval(humans, [preds[i][k] for i in range(N)])
         np.testing.assert_allclose(pe[:, 5:], g["pairs_eval"][k][:, 5:], rtol=1e-6, equal_nan=True)
