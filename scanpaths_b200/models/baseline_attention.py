@@ -285,6 +285,34 @@ class baseline(nn.Module):
         self._decoder = None
         self.eval()
 
+    def attach_encoder(self):
+        """Adds the once-per-image encoder (stays in PyTorch, out of scope of the CUDA path):
+        ResNet-50 with the stride on conv1 of each stage's first block and a ceil-mode max-pool
+        (models/resnet.py:55-103), dilated as in dilate_resnet (baseline_attention.py:212-224),
+        children()[:-2], then sal_conv 3x3 2048 -> 512 (:191-194).  Parameter names match the
+        reference's `resnet.*` / `sal_conv.*` keys."""
+        import torchvision
+        net = torchvision.models.resnet50(weights=None)
+        net.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=0, ceil_mode=True)
+        for layer in (net.layer2, net.layer3, net.layer4):      # torchvision strides conv2, the reference conv1
+            layer[0].conv1.stride, layer[0].conv2.stride = layer[0].conv2.stride, (1, 1)
+        for layer in (net.layer2, net.layer4):
+            layer[0].conv1.stride = (1, 1)
+            layer[0].downsample[0].stride = (1, 1)
+        for block in net.layer3:
+            block.conv2.dilation, block.conv2.padding = (2, 2), (2, 2)
+        for block in net.layer4:
+            block.conv2.dilation, block.conv2.padding = (4, 4), (4, 4)
+        self.resnet = nn.Sequential(*list(net.children())[:-2])
+        self.sal_conv = nn.Conv2d(2048, 512, kernel_size=3, padding=1, stride=1, bias=True)
+        dev = next(self.lstm.parameters()).device
+        self.resnet.to(dev); self.sal_conv.to(dev)
+        self.eval()
+        return self
+
+    def encode(self, images):
+        return F.relu(self.sal_conv(self.resnet(images)))
+
     def load_state_dict(self, state_dict, strict=False, **kw):
         self._decoder = None
         own = {k: v for k, v in state_dict.items() if not k.startswith(("resnet.", "sal_conv."))} \
@@ -313,7 +341,7 @@ class baseline(nn.Module):
         else:
             if self.resnet is None:
                 raise _lib.SpbError("no encoder attached: pass visual_feature [N,512,30,40] or attach_encoder()")
-            vf = F.relu(self.sal_conv(self.resnet(images)))
+            vf = self.encode(images)
         return self.decode(vf, attention_maps, tasks)
 
 

@@ -106,6 +106,28 @@ def structured_to_xyd(fix_vector):
     return np.array([list(r) for r in list(fix_vector)], dtype=np.float64)
 
 
+def pack_subject_lists(batch_fix_vectors, pin=True):
+    """The evaluation datasets' `fix_vectors` (a list per image of per-subject structured arrays,
+    dataset.py `*_evaluation.__getitem__` / `collate_func`) -> dense [N, Smax, Lmax, 3] f64 + lens
+    [N, Smax] i32 (+ n_subjects [N]) in pinned host memory, ready for ScanpathPipeline.set_humans.
+    Images with fewer subjects are padded with empty scanpaths (length 0)."""
+    N = len(batch_fix_vectors)
+    smax = max(len(f) for f in batch_fix_vectors)
+    lmax = max(1, max(len(s) for f in batch_fix_vectors for s in f))
+    xyd = torch.zeros((N, smax, lmax, 3), dtype=torch.float64)
+    lens = torch.zeros((N, smax), dtype=torch.int32)
+    nsub = torch.zeros((N,), dtype=torch.int32)
+    for i, fvs in enumerate(batch_fix_vectors):
+        nsub[i] = len(fvs)
+        for j, fv in enumerate(fvs):
+            a = structured_to_xyd(fv)
+            xyd[i, j, :len(a)] = torch.from_numpy(a)
+            lens[i, j] = len(a)
+    if pin and torch.cuda.is_available():
+        xyd, lens = xyd.pin_memory(), lens.pin_memory()
+    return xyd, lens, nsub
+
+
 def prep_paths(xyd: torch.Tensor, lens: torch.Tensor, cfg: ScoreConfig) -> PathPack:
     """K1: xyd [n,lmax,3] f64 + lens [n] i32 (device tensors) -> PathPack."""
     lib = _lib.load()
