@@ -170,7 +170,7 @@ int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s) {
 // C[M,N] = A[M,K] * B[N,K]^T + bias[N]   (fp32 SIMT; the small per-step GEMMs:
 // spatial_embed, semantic_embed, rank-1 gate projection)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 sgemm_nt_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
                 const float *__restrict__ bias, float *__restrict__ C, int64_t ldc, int M, int N, int K) {
     __shared__ float As[16][64 + 4];
@@ -272,15 +272,17 @@ lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, co
 // 120 pixels, the tile's spatial-memory halo sits in shared memory, and every global access is a
 // fully coalesced 128-byte line per warp (acc / xg: 4 gate segments of 32 channels, gate_col order).
 // Algorithmic HBM traffic: 26.8 MB per image-step (acc 9.8 + xg 9.8 + c 2.4 r + 2.4 w + h 2.4).
+// Blocks are 128 threads (one 128-channel group): small enough (8 K registers, < 1 KB smem) to be
+// co-resident with a persistent GEMM CTA of the other half-wave's stream (see pipeline.py).
 template <int S>
-__global__ void __launch_bounds__(512, S == 1 ? 2 : 1)
+__global__ void __launch_bounds__(128, S == 1 ? 8 : 4)
 lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ xg, const float *__restrict__ V,
                        const float *__restrict__ sp_mem, float *__restrict__ c, __half *__restrict__ h_hi,
                        __half *__restrict__ h_lo) {
     __shared__ float halo[S][5][42];
     const int64_t n = blockIdx.y;
     const int m_tile = blockIdx.x, y0 = m_tile * 3;
-    const int ch = threadIdx.x;
+    const int ch = blockIdx.z * 128 + threadIdx.x;
     for (int i = threadIdx.x; i < S * 210; i += blockDim.x) {
         const int st = i / 210, rem = i - st * 210, hy = rem / 42, hx = rem - hy * 42;
         const int yy = y0 - 1 + hy, xx = hx - 1;
@@ -896,10 +898,10 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             prof_begin(kTagCell, s);
             if (tc) {
                 if (S == 1)
-                    lstm_cell_tiled_kernel<1><<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(
+                    lstm_cell_tiled_kernel<1><<<dim3(kHW / 120, (unsigned)N, kE / 128), 128, 0, s>>>(
                         ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
                 else
-                    lstm_cell_tiled_kernel<2><<<dim3(kHW / 120, (unsigned)N), 512, 0, s>>>(
+                    lstm_cell_tiled_kernel<2><<<dim3(kHW / 120, (unsigned)N, kE / 128), 128, 0, s>>>(
                         ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
             } else {
                 lstm_cell_kernel<<<(unsigned)((NP * kE + 255) / 256), 256, 0, s>>>(ws.acc, ws.xg, ws.V, ws.sp_mem, ws.c,
