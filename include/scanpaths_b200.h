@@ -193,6 +193,8 @@ typedef struct spb_decoder_weights {
     const void *wx_hi, *wx_lo;       /* fp16 [2048, 4608]  lstm.*_x                     */
     const void *wh_hi, *wh_lo;       /* fp16 [2048, 4608]  lstm.*_h                     */
     const void *wp_hi, *wp_lo;       /* fp16 [n_weight_sets*512, 12800]  5x5 layer(s)   */
+    const void *ww_hi, *ww_lo;       /* fp16 [16*2048, 512] Winograd-transformed lstm.*_h: G g G^T, position-major */
+    const int32_t *d_wino_row_base;  /* [16] = position * 2048                          */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
     const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */
@@ -215,7 +217,7 @@ typedef struct spb_decoder_weights {
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;
-    float inv_scale_x, inv_scale_h, inv_scale_p;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
     int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
     int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
     int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
@@ -224,7 +226,8 @@ typedef struct spb_decoder_weights {
 
 typedef struct spb_decoder_io {
     int32_t n_images, steps;
-    int32_t use_tensor_cores;        /* 1: tcgen05 implicit GEMM; 0: SIMT fp32 verification kernel */
+    int32_t use_tensor_cores;        /* 1: tcgen05, Winograd F(2x2,3x3) gate GEMMs + composed head (product path); */
+                                     /* 2: tcgen05 direct 3x3 implicit GEMM + composed head; 0: SIMT fp32 check kernels */
     int32_t reserved;
     const float *d_vf;               /* [N, 512, 30, 40] visual_feature (NCHW, as the encoder emits it) */
     const float *d_att;              /* [N, 1200] initial attention map, or NULL = zeros (OSIE)         */

@@ -54,7 +54,6 @@ constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barrie
 constexpr int kTmemCols = 512, kCorrCol = 256;
 constexpr int kThreads = 320;
 constexpr int kChunkKB = kE / kBlockK;                    // k-blocks per drained chunk: one filter tap
-constexpr int kPT = kHW / kTilePix;                       // 5 pixel tiles per image
 constexpr int kHalfPix = kTilePix / 2;                    // 120 pixels of totals per drain thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +128,7 @@ template <int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                    ConvGemmArgs a, int num_tiles, int nct) {
+                    ConvGemmArgs a, int num_tiles, int nct, int kPT, int rows_per_img) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + kStages * kStageBytes;
@@ -306,7 +305,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             // epilogue: for a fixed pixel the 32 lanes of a warp write 32 consecutive channels (128 B)
             const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
             const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
-            float *dst = a.out + ((int64_t)img * kHW + p_tile * kTilePix + half * kHalfPix) * a.ldo + c_tile * kTileCh + r;
+            float *dst = a.out + ((int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix) * a.ldo + c_tile * kTileCh + r;
 #pragma unroll
             for (int j = 0; j < kHalfPix; ++j) dst[(int64_t)j * a.ldo] = tot[j] * a.inv_scale + bias;
         }
@@ -336,9 +335,9 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images) {
-    const cuuint64_t dims[4] = {(cuuint64_t)kE, (cuuint64_t)kW, (cuuint64_t)kH, (cuuint64_t)n_images};
-    const cuuint64_t strides[3] = {(cuuint64_t)kE * 2, (cuuint64_t)kW * kE * 2, (cuuint64_t)kHW * kE * 2};
+static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images, int rows_per_img) {
+    const cuuint64_t dims[4] = {(cuuint64_t)kE, (cuuint64_t)kW, (cuuint64_t)(rows_per_img / kW), (cuuint64_t)n_images};
+    const cuuint64_t strides[3] = {(cuuint64_t)kE * 2, (cuuint64_t)kW * kE * 2, (cuuint64_t)rows_per_img * kE * 2};
     const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kW, (cuuint32_t)(kTilePix / kW), 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
@@ -362,8 +361,12 @@ static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K
 
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
-    if (a.cols % kTileCh != 0 || (a.ks != 3 && a.ks != 5) || a.mode != 0) {
-        set_error("conv_gemm_tc: cols must be a multiple of %d, ks 3 or 5", kTileCh);
+    // ks = 3 / 5: convolution over 30 x 40 images (rows_per_img = 1200).  ks = 1: plain batched GEMM
+    // out[b][row][col] = sum_k a[b][row][k] w[w_row_base[b] + col][k] with rows_per_img rows per batch
+    // entry (the per-position GEMMs of the Winograd path).
+    const int rows = a.ks == 1 ? a.rows_per_img : kHW;
+    if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || rows <= 0 || rows % kTilePix != 0) {
+        set_error("conv_gemm_tc: cols must be a multiple of %d, rows per image of %d, ks 1, 3 or 5", kTileCh, kTilePix);
         return SPB_ERR_ARG;
     }
     if (get_encode() == nullptr) {
@@ -372,24 +375,29 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     }
     const int64_t K = (int64_t)a.ks * a.ks * kE;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images);
-    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images);
+    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows);
+    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
     if (rc) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
     }
-    const int nct = a.cols / kTileCh;
-    const int num_tiles = nct * kPT * a.n_images;
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
-    if (a.ks == 3) {
-        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        conv_gemm_tc_kernel<3><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, a, num_tiles, nct);
-    } else {
-        SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        conv_gemm_tc_kernel<5><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, a, num_tiles, nct);
+    const int nct = a.cols / kTileCh, pt = rows / kTilePix;
+    const int64_t tiles64 = (int64_t)nct * pt * a.n_images;
+    if (tiles64 > 0x7fffffff) {
+        set_error("conv_gemm_tc: too many tiles");
+        return SPB_ERR_ARG;
     }
+    const int num_tiles = (int)tiles64;
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
+#define SPB_LAUNCH_TC(KS_)                                                                                          \
+    SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, a, num_tiles, nct, pt, rows)
+    if (a.ks == 1) { SPB_LAUNCH_TC(1); }
+    else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
+    else { SPB_LAUNCH_TC(5); }
+#undef SPB_LAUNCH_TC
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }

@@ -31,6 +31,28 @@ __device__ __forceinline__ void split_one(float v, __half &hi, __half &lo) {
     lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
 }
 
+// the exact fp32 value of an fp16 (hi, lo) pair, 4 / 8 consecutive channels
+__device__ __forceinline__ void load_h4(const __half *hi, const __half *lo, int64_t off, float (&v)[4]) {
+    const uint2 a = *reinterpret_cast<const uint2 *>(hi + off), b = *reinterpret_cast<const uint2 *>(lo + off);
+    const __half2 a0 = *reinterpret_cast<const __half2 *>(&a.x), a1 = *reinterpret_cast<const __half2 *>(&a.y);
+    const __half2 b0 = *reinterpret_cast<const __half2 *>(&b.x), b1 = *reinterpret_cast<const __half2 *>(&b.y);
+    const float2 fa0 = __half22float2(a0), fa1 = __half22float2(a1), fb0 = __half22float2(b0), fb1 = __half22float2(b1);
+    v[0] = fa0.x + fb0.x * (1.0f / kLoScale); v[1] = fa0.y + fb0.y * (1.0f / kLoScale);
+    v[2] = fa1.x + fb1.x * (1.0f / kLoScale); v[3] = fa1.y + fb1.y * (1.0f / kLoScale);
+}
+
+__device__ __forceinline__ void load_h8(const __half *hi, const __half *lo, int64_t off, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(hi + off), b = *reinterpret_cast<const uint4 *>(lo + off);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[i]));
+        const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[i]));
+        v[2 * i] = fa.x + fb.x * (1.0f / kLoScale);
+        v[2 * i + 1] = fa.y + fb.y * (1.0f / kLoScale);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int C, int HW,
                        float scale) {
@@ -334,6 +356,158 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// Winograd F(2x2, 3x3) for the 3x3 gate convolution of h (product path).
+//   Y = A^T [ (G g G^T) (.) (B^T d B) ] A   per 2x2 output tile and (ci, co) pair, summed over ci:
+//   16 multiplies per 4 outputs instead of 36 -> 2.25x fewer tensor-core MMAs.  The per-position
+//   sums over ci are 16 independent GEMMs [tiles x 512] x [512 x 2048] (conv_tc.cu, ks = 1); the
+//   input transform (adds only) runs here in fp32 on the exact 22-bit h values and is re-split into
+//   fp16 pairs, the weight transform is done once in float64 (prepare_weights), and the output
+//   transform is folded into the cell kernel below.  Emulated end to end, the representation error
+//   of this path is 1.4e-7 rms on the convolution -- far inside the parity gate.
+// Tiles: image 30 x 40 -> 15 x 20 tiles; input tile rows 2ty-1 .. 2ty+2, cols 2tx-1 .. 2tx+2.
+// ---------------------------------------------------------------------------
+constexpr int kTilesY = 15, kTilesX = 20, kTilesPerImg = 300;
+
+// U[pos][n*300 + tile][ci] = (B^T d B)[pos]; one block per (image, tile), thread = 4 channels.
+__global__ void __launch_bounds__(128)
+wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, __half *__restrict__ u_hi,
+                  __half *__restrict__ u_lo, int64_t rows_pad) {
+    const int64_t nt = blockIdx.x;                   // n*300 + tile
+    const int64_t n = nt / kTilesPerImg;
+    const int tile = (int)(nt - n * kTilesPerImg);
+    const int ty = tile / kTilesX, tx = tile - ty * kTilesX;
+    const int c0 = threadIdx.x * 4;
+    float d[4][4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int yy = 2 * ty - 1 + a, xx = 2 * tx - 1 + b;
+            if (yy >= 0 && yy < kH && xx >= 0 && xx < kW) {
+                load_h4(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + c0, d[a][b]);
+            } else {
+                d[a][b][0] = d[a][b][1] = d[a][b][2] = d[a][b][3] = 0.0f;
+            }
+        }
+    // rows: B^T d  (r0 = d0 - d2, r1 = d1 + d2, r2 = d2 - d1, r3 = d1 - d3), then columns
+    float u[4][4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            u[0][b][e] = d[0][b][e] - d[2][b][e];
+            u[1][b][e] = d[1][b][e] + d[2][b][e];
+            u[2][b][e] = d[2][b][e] - d[1][b][e];
+            u[3][b][e] = d[1][b][e] - d[3][b][e];
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float t0 = u[i][0][e] - u[i][2][e], t1 = u[i][1][e] + u[i][2][e];
+            const float t2 = u[i][2][e] - u[i][1][e], t3 = u[i][1][e] - u[i][3][e];
+            u[i][0][e] = t0; u[i][1][e] = t1; u[i][2][e] = t2; u[i][3][e] = t3;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __half hh[4], hl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_one(u[i][j][e], hh[e], hl[e]);
+            const int64_t off = ((int64_t)(i * 4 + j) * rows_pad + nt) * kE + c0;
+            *reinterpret_cast<uint2 *>(u_hi + off) =
+                make_uint2((uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16),
+                           (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16));
+            *reinterpret_cast<uint2 *>(u_lo + off) =
+                make_uint2((uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16),
+                           (uint32_t)__half_as_ushort(hl[2]) | ((uint32_t)__half_as_ushort(hl[3]) << 16));
+        }
+}
+
+// ConvLSTM cell with the Winograd output transform folded in: block = (tile row ty, image, 128-channel
+// group), thread = channel, loop over the 20 tiles of the row; per tile and gate the 16 per-position
+// GEMM results m[pos] (coalesced 128-byte lines) give the 2x2 pre-activations A^T m A.
+// M == NULL means h = 0 (first step).  HBM: 16 x 8 KB (M) + 4 x 8 KB (xg) + c, h per tile.
+template <int S>
+__global__ void __launch_bounds__(128)
+lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ xg,
+                      const float *__restrict__ V, const float *__restrict__ sp_mem, float *__restrict__ c,
+                      __half *__restrict__ h_hi, __half *__restrict__ h_lo) {
+    __shared__ float halo[S][4][42];
+    const int64_t n = blockIdx.y;
+    const int ty = blockIdx.x;
+    const int ch = blockIdx.z * 128 + threadIdx.x;
+    for (int i = threadIdx.x; i < S * 168; i += blockDim.x) {
+        const int st = i / 168, rem = i - st * 168, hy = rem / 42, hx = rem - hy * 42;
+        const int yy = 2 * ty - 1 + hy, xx = hx - 1;
+        halo[st][hy][hx] = (yy >= 0 && yy < kH && xx >= 0 && xx < kW) ? sp_mem[(n * S + st) * kHW + yy * kW + xx] : 0.0f;
+    }
+    float v[S][3][9];
+#pragma unroll
+    for (int st = 0; st < S; ++st)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9)
+                v[st][g][t9] = V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9];
+    __syncthreads();
+    const int gc = gate_col(ch, 0);
+    for (int tx = 0; tx < kTilesX; ++tx) {
+        float pre[4][4];                              // [gate][oy*2 + ox]
+        const int64_t row = n * kTilesPerImg + ty * kTilesX + tx;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float m[16];
+#pragma unroll
+            for (int pos = 0; pos < 16; ++pos)
+                m[pos] = M ? M[((int64_t)pos * rows_pad + row) * kGateCols + gc + g * 32] : 0.0f;
+            float t[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                t[i][0] = (m[4 * i] + m[4 * i + 1]) + m[4 * i + 2];
+                t[i][1] = (m[4 * i + 1] - m[4 * i + 2]) - m[4 * i + 3];
+            }
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+                pre[g][ox] = (t[0][ox] + t[1][ox]) + t[2][ox];
+                pre[g][2 + ox] = (t[1][ox] - t[2][ox]) - t[3][ox];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int oy = q >> 1, ox = q & 1;
+            const int64_t pix = n * kHW + (2 * ty + oy) * kW + 2 * tx + ox;
+            const float *xp = xg + pix * kGateCols + gc;
+            float p0 = pre[0][q] + xp[0], p1 = pre[1][q] + xp[32], p2 = pre[2][q] + xp[64];
+            const float p3 = pre[3][q] + xp[96];
+            const float cold = c[pix * kE + ch];
+#pragma unroll
+            for (int st = 0; st < S; ++st) {
+                float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    const float sv = halo[st][oy + t9 / 3][2 * tx + ox + t9 % 3];
+                    r0 = fmaf(v[st][0][t9], sv, r0);
+                    r1 = fmaf(v[st][1][t9], sv, r1);
+                    r2 = fmaf(v[st][2][t9], sv, r2);
+                }
+                p0 += r0; p1 += r1; p2 += r2;
+            }
+            const float gi = __frcp_rn(1.0f + __expf(-p0));
+            const float gf = __frcp_rn(1.0f + __expf(-p1));
+            const float go = __frcp_rn(1.0f + __expf(-p2));
+            const float gg = 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * p3));
+            const float cn = gf * cold + gi * gg;
+            c[pix * kE + ch] = cn;
+            __half hh, hl;
+            split_one(go * cn, hh, hl);
+            h_hi[pix * kE + ch] = hh; h_lo[pix * kE + ch] = hl;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Head, part 1 (predict_head.forward :141-150): per pixel, the channel dot products of
 // feat with sal_layer_2, sal_layer_3 and with the <= 4 drt_layer_1 taps under which the
 // pixel falls (7x7 kernel, stride 5, pad 2 -> 6x8 windows).  One warp per (image, head, pixel).
@@ -393,26 +567,7 @@ head_reduce_kernel(const float *__restrict__ feat, int HD, const float *__restri
 // with effective kernels composed once in float64 (prepare_weights).  h is read as the same fp16
 // (hi, lo) pair the gate GEMM consumes.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void load_h4(const __half *hi, const __half *lo, int64_t off, float (&v)[4]) {
-    const uint2 a = *reinterpret_cast<const uint2 *>(hi + off), b = *reinterpret_cast<const uint2 *>(lo + off);
-    const __half2 a0 = *reinterpret_cast<const __half2 *>(&a.x), a1 = *reinterpret_cast<const __half2 *>(&a.y);
-    const __half2 b0 = *reinterpret_cast<const __half2 *>(&b.x), b1 = *reinterpret_cast<const __half2 *>(&b.y);
-    const float2 fa0 = __half22float2(a0), fa1 = __half22float2(a1), fb0 = __half22float2(b0), fb1 = __half22float2(b1);
-    v[0] = fa0.x + fb0.x * (1.0f / kLoScale); v[1] = fa0.y + fb0.y * (1.0f / kLoScale);
-    v[2] = fa1.x + fb1.x * (1.0f / kLoScale); v[3] = fa1.y + fb1.y * (1.0f / kLoScale);
-}
 
-__device__ __forceinline__ void load_h8(const __half *hi, const __half *lo, int64_t off, float (&v)[8]) {
-    const uint4 a = *reinterpret_cast<const uint4 *>(hi + off), b = *reinterpret_cast<const uint4 *>(lo + off);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[i]));
-        const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[i]));
-        v[2 * i] = fa.x + fb.x * (1.0f / kLoScale);
-        v[2 * i + 1] = fa.y + fb.y * (1.0f / kLoScale);
-    }
-}
 
 // y2[p], y3[p] for a 3-row pixel tile of one (image, head): a register-tiled direct convolution.
 // Per 64-channel chunk the 7 x 44 halo of h (fp32, rebuilt from the hi/lo pair, zero outside the
@@ -722,7 +877,9 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 
 // ---------------------------------------------------------------------------
 struct Workspace {
-    __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2];
+    __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2], *u_hi, *u_lo;
+    float *wm;             // Winograd per-position GEMM results [16][rows_pad][2048]
+    int64_t rows_pad;
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
     int64_t bytes;
@@ -763,6 +920,10 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.sp_mem = (float *)take(N * S * kHW * 4);
     w.se_mem = (float *)take(N * S * kE * 4);
     w.drt_pre = (float *)take(N * HD * 48 * 4);
+    w.rows_pad = (N * kTilesPerImg + 239) / 240 * 240;
+    w.u_hi = (__half *)take(16 * w.rows_pad * kE * 2);
+    w.u_lo = (__half *)take(16 * w.rows_pad * kE * 2);
+    w.wm = (float *)take(16 * w.rows_pad * (int64_t)kGateCols * 4);
     w.bytes = o;
     return w;
 }
@@ -804,9 +965,11 @@ extern "C" int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void 
                              int64_t ldo, int32_t n_images, int32_t cols, int32_t ks, float inv_scale,
                              int32_t use_tensor_cores, spb_stream stream) {
     SPB_CHECK_ARG(d_a_hi && d_a_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
-    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
+    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 1 || ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
+    SPB_CHECK_ARG(ks != 1 || use_tensor_cores != 0, "ks = 1 (batched GEMM, 1200 rows per entry) needs the tensor-core path");
     ConvGemmArgs a{(const __half *)d_a_hi, (const __half *)d_a_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
                    d_w_row_base, w_rows, d_bias, d_out, ldo, n_images, cols, ks, inv_scale};
+    a.rows_per_img = kHW;
     return conv_gemm(a, use_tensor_cores != 0, (cudaStream_t)stream);
 }
 
@@ -832,6 +995,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     }
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = io->use_tensor_cores != 0;
+    const bool wino = io->use_tensor_cores == 1;       // 1: Winograd gate GEMMs (product path); 2: direct 3x3 GEMM
     const int64_t NP = N * kHW;
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
@@ -881,20 +1045,45 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
                              ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
         prof_end(s);
-        // 3x3 gate convolutions of h, then the ConvLSTM cell
         const int cur = t & 1, nxt = cur ^ 1;
-        prof_begin(kTagConvH, s);
-        {
-            ConvGemmArgs a{ws.h_hi[cur], ws.h_lo[cur], (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr,
-                           kGateCols, nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
-            if (t == 0 && a.mode == 0) {
+        if (wino) {
+            // 3x3 gate convolutions of h as Winograd F(2x2,3x3): input transform, 16 per-position GEMMs
+            // on tcgen05, output transform folded into the ConvLSTM cell.  h(0) = 0 -> nothing to multiply.
+            if (t > 0) {
+                prof_begin(kTagCell, s);
+                wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 128, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
+                                                                             ws.rows_pad);
+                SPB_LAUNCH_CHECK();
+                prof_end(s);
+                prof_begin(kTagConvH, s);
+                ConvGemmArgs a{ws.u_hi, ws.u_lo, (const __half *)w->ww_hi, (const __half *)w->ww_lo, w->d_wino_row_base,
+                               16 * (int64_t)kGateCols, nullptr, ws.wm, kGateCols, 16, kGateCols, 1, w->inv_scale_w};
+                a.rows_per_img = (int)ws.rows_pad;
+                SPB_TRY(conv_gemm_tc(a, s));
+                prof_end(s);
+            }
+            prof_begin(kTagCell, s);
+            const float *Mp = t > 0 ? ws.wm : nullptr;
+            if (S == 1)
+                lstm_cell_wino_kernel<1><<<dim3(kTilesY, (unsigned)N, kE / 128), 128, 0, s>>>(
+                    Mp, ws.rows_pad, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
+            else
+                lstm_cell_wino_kernel<2><<<dim3(kTilesY, (unsigned)N, kE / 128), 128, 0, s>>>(
+                    Mp, ws.rows_pad, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
+            SPB_LAUNCH_CHECK();
+            prof_end(s);
+        } else {
+            // 3x3 gate convolutions of h as a direct implicit GEMM (tcgen05 with use_tensor_cores = 2,
+            // SIMT fp32 on the verification route), then the ConvLSTM cell
+            prof_begin(kTagConvH, s);
+            if (t == 0) {
                 SPB_CUDA(cudaMemsetAsync(ws.acc, 0, NP * kGateCols * 4, s));   // h(0) = 0: its convolution is exactly 0
             } else {
+                ConvGemmArgs a{ws.h_hi[cur], ws.h_lo[cur], (const __half *)w->wh_hi, (const __half *)w->wh_lo, nullptr,
+                               kGateCols, nullptr, ws.acc, kGateCols, (int)N, kGateCols, 3, w->inv_scale_h};
                 SPB_TRY(conv_gemm(a, tc, s));
             }
-        }
-        prof_end(s);
-        {
+            prof_end(s);
             prof_begin(kTagCell, s);
             if (tc) {
                 if (S == 1)

@@ -15,6 +15,7 @@ constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
 //   w  = w_hi + w_lo / 2^11   fp16 [rows, ks*ks*512], K index = (ky*ks+kx)*512 + ci, pre-multiplied by 1/inv_scale
 //   row of w used for output column `col` of image n:  w_row_base[n] + col   (w_row_base NULL -> 0)
+// ks = 1 turns the kernel into a plain batched GEMM (n_images = batch, rows_per_img rows each).
 struct ConvGemmArgs {
     const __half *a_hi, *a_lo;
     const __half *w_hi, *w_lo;
@@ -25,7 +26,7 @@ struct ConvGemmArgs {
     int64_t ldo;
     int n_images, cols, ks;
     float inv_scale;
-    int mode = 0;                     // reserved (0)
+    int rows_per_img = 0;             // ks = 1 only: rows per batch entry (multiple of 240)
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].

@@ -75,6 +75,14 @@ def prepare_weights(sd, task: str, device):
     wx = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_X])
     wh = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_H])
     wp = torch.cat([_conv_to_gemm(f(s + ".weight")) for s in sets], 0).contiguous()
+    # Winograd F(2x2,3x3) weights of the h-gates: W'[pos = 4i+j] = (G g G^T)[i][j], composed in float64,
+    # rows gate-interleaved like wh, position-major: [16 * 2048, 512]
+    Gm = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64, device=device)
+    wino = [torch.einsum("ia,ocab,jb->oijc", Gm, f("lstm.%s.weight" % g).double(), Gm).reshape(512, 16 * 512)
+            for g in GATES_H]
+    ww = _interleave_gates(wino).view(2048, 16, 512).permute(1, 0, 2).reshape(16 * 2048, 512)
+    t["ww_hi"], t["ww_lo"], isw = split_pair(ww)
+    t["d_wino_row_base"] = (torch.arange(16, device=device, dtype=torch.int32) * 2048).contiguous()
     t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
     t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
     t["wp_hi"], t["wp_lo"], isp = split_pair(wp)
@@ -144,7 +152,7 @@ def prepare_weights(sd, task: str, device):
         "object_head.drt_layer_1.bias")
     bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
     w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
-    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p = isx, ish, isp
+    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w = isx, ish, isp, isw
     w.n_streams = w.n_heads = len(streams)
     w.n_weight_sets = len(sets)
     return t, w
@@ -158,7 +166,7 @@ class CudaDecoder:
         self.lib = _lib.load()
         self.task, self.steps, self.wave = task, int(steps), int(wave)
         self.device = torch.device(device)
-        self.use_tensor_cores = int(use_tensor_cores)     # 0 = SIMT check path (explicit 5x5 layer), 1 = tcgen05 + composed head
+        self.use_tensor_cores = int(use_tensor_cores)     # 0 = SIMT check path (explicit 5x5 layer), 1 = tcgen05 Winograd + composed head, 2 = tcgen05 direct 3x3
         self.tensors, self.w = prepare_weights(state_dict, task, self.device)
         self.heads = int(self.w.n_heads)
         self._ws, self._ws_n = None, 0

@@ -22,6 +22,29 @@ def lib():
     return _lib.load()
 
 
+def test_batched_gemm_mode_ks1(lib):
+    """ks = 1: the kernel as a plain batched GEMM (the per-position GEMMs of the Winograd path)."""
+    from scanpaths_b200 import _lib
+    from scanpaths_b200.models.baseline_attention import split_pair
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    B, cols = 3, 256
+    a = torch.randn(B, 1200, 512, generator=g, device=dev)
+    w = torch.randn(B * cols, 512, generator=g, device=dev) * 0.05
+    a_hi = torch.empty_like(a, dtype=torch.float16); a_lo = torch.empty_like(a_hi)
+    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0,
+                                  _lib.current_stream()), "split")
+    w_hi, w_lo, inv = split_pair(w)
+    base = (torch.arange(B, device=dev, dtype=torch.int32) * cols).contiguous()
+    out = torch.empty((B * 1200, cols), device=dev)
+    _lib.check(lib.spb_conv_gemm(_lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(base),
+                                 B * cols, None, _lib.ptr(out), cols, B, cols, 1, inv, 1, _lib.current_stream()),
+               "spb_conv_gemm")
+    ref = torch.einsum("brk,bck->brc", a.double(), w.double().view(B, cols, 512)).reshape(B * 1200, cols)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-6 * ref.abs().max().item(), err
+
+
 def _conv_case(lib, ks, n_images, cols, use_tc, per_image_sets=0, seed=0):
     from scanpaths_b200 import _lib
     from scanpaths_b200.models.baseline_attention import split_pair
@@ -108,12 +131,13 @@ def _decode_case(name, use_tc, golden_dir, steps=None):
 
 
 @pytest.mark.parametrize("name", ["coco", "air", "osie"])
-@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
     """use_tc: 0 = SIMT fp32 check kernels with the explicit 5x5 layer (an independent route to the
-    same numbers), 1 = the product path (tcgen05 gate GEMM + composed head)."""
+    same numbers), 1 = the product path (tcgen05 Winograd gate GEMMs + composed head), 2 = tcgen05
+    direct 3x3 implicit GEMM + composed head."""
     worst = _decode_case(name, use_tc, golden_dir)
-    print(name, ["simt", "tc"][use_tc], worst)
+    print(name, ["simt", "tc-winograd", "tc-direct"][use_tc], worst)
     for k, v in worst.items():
         if k.endswith("ref_f32_prob"):
             continue
