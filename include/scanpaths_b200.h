@@ -193,7 +193,8 @@ typedef struct spb_decoder_weights {
     const void *wx_hi, *wx_lo;       /* fp16 [2048, 4608]  lstm.*_x                     */
     const void *wh_hi, *wh_lo;       /* fp16 [2048, 4608]  lstm.*_h                     */
     const void *wp_hi, *wp_lo;       /* fp16 [n_weight_sets*512, 12800]  5x5 layer(s)   */
-    const void *ww_hi, *ww_lo;       /* fp16 [16*2048, 512] Winograd-transformed lstm.*_h: G g G^T, position-major */
+    const void *ww_hi, *ww_lo;       /* fp16 [16*2048, 512] Winograd-transformed lstm.*_h: G g G^T, position-major, */
+                                     /*   UNSCALED low half: w * scale = hi + lo           */
     const int32_t *d_wino_row_base;  /* [16] = position * 2048                          */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
@@ -249,9 +250,11 @@ int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, co
                   int32_t n_images, int32_t cols, int32_t ks, float inv_scale, int32_t use_tensor_cores,
                   spb_stream stream);
 
-/* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11; NCHW [N,C,HW] -> NHWC when `transpose`. */
+/* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11 (lo_unscaled = 0, operands of the ks = 3 / 5
+ * convolutions) or x*scale = hi + lo (lo_unscaled = 1, operands of the ks = 1 batched GEMM; the caller
+ * picks `scale` so that lo stays a normal fp16).  NCHW [N,C,HW] -> NHWC when `transpose`. */
 int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
-                   int32_t transpose, float scale, spb_stream stream);
+                   int32_t transpose, float scale, int32_t lo_unscaled, spb_stream stream);
 
 #ifdef __cplusplus
 }

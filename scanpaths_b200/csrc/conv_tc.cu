@@ -50,11 +50,14 @@ static_assert(kSwizzleBytes == 128 || kSwizzleBytes == 64, "BLOCK_K must be 64 o
 constexpr int kWBytes = kTileCh * kBlockK * 2;            // 16 KB per weight operand tile
 constexpr int kActBytes = kTilePix * kBlockK * 2;         // 30 KB per activation operand tile
 constexpr int kStageBytes = 2 * kWBytes + 2 * kActBytes;  // 92 KB: W_hi, W_lo, A_hi, A_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kOutRows = 30;                              // pixels per TMA-store box
+constexpr int kOutBytes = kOutRows * kTileCh * 4;         // 15 KB staging per pixel half
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kOutBytes;
 constexpr int kTmemCols = 512, kCorrCol = 256;
 constexpr int kThreads = 320;
 constexpr int kChunkKB = kE / kBlockK;                    // k-blocks per drained chunk: one filter tap
 constexpr int kHalfPix = kTilePix / 2;                    // 120 pixels of totals per drain thread
+static_assert(kHalfPix % kOutRows == 0, "store boxes must tile the pixel half");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +86,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -124,11 +132,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr));
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                    ConvGemmArgs a, int num_tiles, int nct, int kPT, int rows_per_img) {
+                    const __grid_constant__ CUtensorMap tmOut, ConvGemmArgs a, int num_tiles, int nct, int kPT, int rows_per_img) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + kStages * kStageBytes;
@@ -137,7 +149,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t main_full_bar = bar0 + 8 * (2 * kStages);        // MMA -> drain warps: one tap accumulated
     const uint32_t main_empty_bar = bar0 + 8 * (2 * kStages + 1);   // drain warps -> MMA: accumulator 0 read out
     const uint32_t corr_empty_bar = bar0 + 8 * (2 * kStages + 2);   // drain warps -> MMA: accumulator 1 read out
-    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 3);
+    const uint32_t corr_full_bar = bar0 + 8 * (2 * kStages + 3);    // MMA -> drain warps: accumulator 1 of the tile complete
+    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 4);
+    const uint32_t out_smem = bar0 + 256;                         // 2 x 15 KB TMA-store staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kNumKB = KS * KS * (kE / kBlockK);
@@ -149,10 +163,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(main_full_bar, 1);
         mbar_init(main_empty_bar, 8);
         mbar_init(corr_empty_bar, 8);
+        mbar_init(corr_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -225,6 +241,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             umma_f16(d_corr, w_hi + adv, x_lo + adv, k > 0 ? 1u : 0u);
                             umma_f16(d_corr, w_lo + adv, x_hi + adv, 1u);
                         }
+                    } else if (kb == kNumKB - 1) {
+                        // last k-block of the tile: finish accumulator 0 first and publish it, so that its
+                        // drain overlaps the last correction MMAs
+                        if (kc == 0) {
+                            mbar_wait(main_empty_bar, (gch - 1) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_main, w_hi + adv, x_hi + adv, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(main_full_bar);
+                        ++gch;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            umma_f16(d_corr, w_hi + adv, x_lo + adv, 1u);
+                            umma_f16(d_corr, w_lo + adv, x_hi + adv, 1u);
+                        }
+                        umma_commit(corr_full_bar);
                     } else {
                         // correction products first: they do not touch accumulator 0, which the drain
                         // warps may still be reading at a chunk boundary
@@ -245,7 +282,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         }
                     }
                     umma_commit(empty_bar(s));            // frees this smem stage once the MMAs have read it
-                    if (kc == kChunkKB - 1) { umma_commit(main_full_bar); ++gch; }   // this tap's partial sum is complete
+                    if (kc == kChunkKB - 1 && kb != kNumKB - 1) { umma_commit(main_full_bar); ++gch; }   // this tap's partial sum is complete
                 }
             }
         }
@@ -255,60 +292,258 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int half = (warp - 2) >> 2;             // pixel half of the tile: warps 2-5 -> 0, warps 6-9 -> 1
         const int r = q * 32 + lane;                  // output channel (row of the weight tile)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * kHalfPix;
-        uint32_t gch = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t gch = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
             float tot[kHalfPix];
-#pragma unroll
-            for (int j = 0; j < kHalfPix; ++j) tot[j] = 0.0f;
             for (int chunk = 0; chunk < kNumChunks; ++chunk, ++gch) {
                 mbar_wait(main_full_bar, gch & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (chunk == 0) {
+                    // first tap: the totals ARE the accumulator -- all loads in flight, one wait
 #pragma unroll
-                for (int c = 0; c < kHalfPix; c += 24) {
-                    uint32_t v0[8], v1[8], v2[8];
-                    tmem_ld8(lane_addr + c, v0);
-                    tmem_ld8(lane_addr + c + 8, v1);
-                    tmem_ld8(lane_addr + c + 16, v2);
+                    for (int c = 0; c < kHalfPix; c += 8) {
+                        uint32_t v[8];
+                        tmem_ld8(lane_addr + c, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) tot[c + j] = __uint_as_float(v[j]);
+                    }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        tot[c + j] += __uint_as_float(v0[j]);
-                        tot[c + 8 + j] += __uint_as_float(v1[j]);
-                        tot[c + 16 + j] += __uint_as_float(v2[j]);
+                    for (int c = 0; c < kHalfPix; c += 24) {
+                        uint32_t v0[8], v1[8], v2[8];
+                        tmem_ld8(lane_addr + c, v0);
+                        tmem_ld8(lane_addr + c + 8, v1);
+                        tmem_ld8(lane_addr + c + 16, v2);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            tot[c + j] += __uint_as_float(v0[j]);
+                            tot[c + 8 + j] += __uint_as_float(v1[j]);
+                            tot[c + 16 + j] += __uint_as_float(v2[j]);
+                        }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(main_empty_bar) : "memory");
             }
-            // the last main_full commit also covers every correction MMA of this tile: fold accumulator 1
-            // into the totals and hand TMEM back, then run the epilogue from registers
+            // accumulator 1 (all correction products of the tile): fold into the totals, hand TMEM back
+            mbar_wait(corr_full_bar, ti & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < kHalfPix; c += 24) {
-                uint32_t v0[8], v1[8], v2[8];
+            for (int c = 0; c < kHalfPix; c += 40) {
+                uint32_t v0[8], v1[8], v2[8], v3[8], v4[8];
                 tmem_ld8(lane_addr + kCorrCol + c, v0);
                 tmem_ld8(lane_addr + kCorrCol + c + 8, v1);
                 tmem_ld8(lane_addr + kCorrCol + c + 16, v2);
+                tmem_ld8(lane_addr + kCorrCol + c + 24, v3);
+                tmem_ld8(lane_addr + kCorrCol + c + 32, v4);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     tot[c + j] += __uint_as_float(v0[j]) * (1.0f / kLoScale);
                     tot[c + 8 + j] += __uint_as_float(v1[j]) * (1.0f / kLoScale);
                     tot[c + 16 + j] += __uint_as_float(v2[j]) * (1.0f / kLoScale);
+                    tot[c + 24 + j] += __uint_as_float(v3[j]) * (1.0f / kLoScale);
+                    tot[c + 32 + j] += __uint_as_float(v4[j]) * (1.0f / kLoScale);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(corr_empty_bar) : "memory");
 
-            // epilogue: for a fixed pixel the 32 lanes of a warp write 32 consecutive channels (128 B)
+            // epilogue: each pixel half (4 warps = 128 channels) stages 30 pixels x 128 channels in shared
+            // memory and one thread hands the box to the TMA store engine; the 4-byte-per-lane global
+            // stores this replaces kept the drain warps busy for ~6k cycles per tile, longer than a
+            // K = 512 tile of the Winograd path can hide.
             const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
             const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
-            float *dst = a.out + ((int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix) * a.ldo + c_tile * kTileCh + r;
+            const uint32_t stage_out = out_smem + half * kOutBytes;
+            const int64_t row0 = (int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix;
 #pragma unroll
-            for (int j = 0; j < kHalfPix; ++j) dst[(int64_t)j * a.ldo] = tot[j] * a.inv_scale + bias;
+            for (int rr = 0; rr < kHalfPix / kOutRows; ++rr) {
+                if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
+                named_bar_sync(1 + half, 128);
+#pragma unroll
+                for (int j = 0; j < kOutRows; ++j) {
+                    const float v = tot[rr * kOutRows + j] * a.inv_scale + bias;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_out + (uint32_t)(j * kTileCh + r) * 4), "f"(v) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + half, 128);
+                if (r == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmOut), "r"(stage_out), "r"(c_tile * kTileCh), "r"((int)(row0 + rr * kOutRows))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
         }
+        if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores landed before exit
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Flat batched GEMM for the Winograd path (ks = 1): out[b][row][col] = sum_k a[b][row][k] w[base_b + col][k],
+// K = 512.  Same tile (128 channels x 240 rows), same TMA / UMMA staging, but:
+//   * K is only 32 k-steps, so one TMEM accumulator per tile is safe (no mid-K drain), and the
+//     operand pairs use an UNSCALED low half (x*s = hi + lo, see spb_split_fp16 lo_unscaled): all three
+//     products hi*hi + hi*lo + lo*hi accumulate into the SAME accumulator;
+//   * that leaves room for TWO accumulators (2 x 240 of the 512 TMEM columns): the drain warps read
+//     tile i (TMEM -> registers costs ~2k cycles per accumulator at 64 B/clk) and run its epilogue
+//     while the tensor core already works on tile i+1.  With the two-accumulator scheme of the
+//     convolution kernel the drains of these short tiles left the tensor pipe idle 33 % of the time.
+//   * measured (B200): 5.7 ms per 256 images and step; 4.6 ms (the MMA bound) with the stores disabled --
+//     what is left is the cost of streaming 10 GB of per-position results to HBM, whatever the store
+//     mechanism (plain st.global, 15 KB TMA boxes per half, 3.8 KB boxes per warp: all within 3 %).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                    const __grid_constant__ CUtensorMap tmOut, ConvGemmArgs a, int num_tiles, int nct, int kPT,
+                    int rows_per_img) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bar0 + 8 * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8 * (kStages + s); };
+    auto acc_full_bar = [&](int b) { return bar0 + 8 * (2 * kStages + b); };        // MMA -> drain warps
+    auto acc_empty_bar = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };   // drain warps -> MMA
+    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 4);
+    const uint32_t out_smem = bar0 + 256;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kNumKB = kE / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
+                const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
+                const int y0 = p_tile * (kTilePix / kW);
+                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+                    const uint32_t sa = base + s * kStageBytes;
+                    mbar_expect_tx(full_bar(s), kStageBytes);
+                    tma_load_2d(sa, &tmW_hi, full_bar(s), kb * kBlockK, row_base);
+                    tma_load_2d(sa + kWBytes, &tmW_lo, full_bar(s), kb * kBlockK, row_base);
+                    tma_load_4d(sa + 2 * kWBytes, &tmA_hi, full_bar(s), kb * kBlockK, 0, y0, img);
+                    tma_load_4d(sa + 2 * kWBytes + kActBytes, &tmA_lo, full_bar(s), kb * kBlockK, 0, y0, img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti & 1;
+                const uint32_t d_acc = tmem_base + buf * kCorrCol;
+                mbar_wait(acc_empty_bar(buf), ((ti >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(full_bar(s), (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = base + s * kStageBytes;
+                    const uint64_t w_hi = umma_desc_sw128(sa), w_lo = umma_desc_sw128(sa + kWBytes);
+                    const uint64_t x_hi = umma_desc_sw128(sa + 2 * kWBytes), x_lo = umma_desc_sw128(sa + 2 * kWBytes + kActBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        // small terms first, then the leading product
+                        umma_f16(d_acc, w_hi + adv, x_lo + adv, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(d_acc, w_lo + adv, x_hi + adv, 1u);
+                        umma_f16(d_acc, w_hi + adv, x_hi + adv, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc_full_bar(buf));
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        uint64_t evict_first;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
+            const int buf = ti & 1;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kCorrCol + half * kHalfPix;
+            float tot[kHalfPix];
+            mbar_wait(acc_full_bar(buf), (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < kHalfPix; c += 8) {
+                uint32_t v[8];
+                tmem_ld8(lane_addr + c, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tot[c + j] = __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_bar(buf)) : "memory");
+
+            const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
+            const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
+            // every drain warp stores its own 32-channel x 30-pixel boxes (own staging slice, own bulk
+            // group, no cross-warp barrier); the 10 GB of per-position results stream through L2 once,
+            // so they are marked evict-first to keep the weights and activation rows resident
+            const uint32_t stage_out = out_smem + (uint32_t)(warp - 2) * (kOutRows * 32 * 4);
+            const int64_t row0 = (int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix;
+#pragma unroll
+            for (int rr = 0; rr < kHalfPix / kOutRows; ++rr) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kOutRows; ++j) {
+                    const float v = tot[rr * kOutRows + j] * a.inv_scale + bias;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_out + (uint32_t)(j * 32 + lane) * 4), "f"(v) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                        ::"l"(&tmOut), "r"(stage_out), "r"(c_tile * kTileCh + q * 32), "r"((int)(row0 + rr * kOutRows)),
+                          "l"(evict_first)
+                        : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -357,15 +592,28 @@ static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, int box_cols) {
+    const cuuint64_t dims[2] = {(cuuint64_t)ldo, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldo * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kOutRows};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 }  // namespace tc
 
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
-    // ks = 3 / 5: convolution over 30 x 40 images (rows_per_img = 1200).  ks = 1: plain batched GEMM
+    // ks = 3 / 5: convolution over 30 x 40 images (rows_per_img = 1200), operand pairs x = hi + lo / 2^11.
+    // ks = 1: plain batched GEMM (gemm_tc_flat_kernel), operand pairs with UNSCALED low half x = hi + lo;
     // out[b][row][col] = sum_k a[b][row][k] w[w_row_base[b] + col][k] with rows_per_img rows per batch
     // entry (the per-position GEMMs of the Winograd path).
     const int rows = a.ks == 1 ? a.rows_per_img : kHW;
-    if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || rows <= 0 || rows % kTilePix != 0) {
+    if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || rows <= 0 || rows % kTilePix != 0 ||
+        a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0) {
         set_error("conv_gemm_tc: cols must be a multiple of %d, rows per image of %d, ks 1, 3 or 5", kTileCh, kTilePix);
         return SPB_ERR_ARG;
     }
@@ -374,11 +622,12 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
         return SPB_ERR_CUDA;
     }
     const int64_t K = (int64_t)a.ks * a.ks * kE;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo;
     int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows);
     if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
+    if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, a.ks == 1 ? 32 : kTileCh);
     if (rc) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
@@ -393,9 +642,11 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
 #define SPB_LAUNCH_TC(KS_)                                                                                          \
     SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, a, num_tiles, nct, pt, rows)
-    if (a.ks == 1) { SPB_LAUNCH_TC(1); }
-    else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
+    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
+    if (a.ks == 1) {
+        SPB_CUDA(cudaFuncSetAttribute(gemm_tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        gemm_tc_flat_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows);
+    } else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
     else { SPB_LAUNCH_TC(5); }
 #undef SPB_LAUNCH_TC
     SPB_LAUNCH_CHECK();

@@ -76,12 +76,19 @@ split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi, __h
     }
 }
 
+// unscaled low half: v = hi + lo (used where the caller pre-scales v so that lo stays a normal fp16)
+__device__ __forceinline__ void split_one_unscaled(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
 __global__ void __launch_bounds__(256)
 split_plain_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int64_t total,
-                   float scale) {
+                   float scale, int lo_unscaled) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         __half h, l;
-        split_one(x[i] * scale, h, l);
+        if (lo_unscaled) split_one_unscaled(x[i] * scale, h, l);
+        else split_one(x[i] * scale, h, l);
         hi[i] = h; lo[i] = l;
     }
 }
@@ -367,6 +374,9 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
 // Tiles: image 30 x 40 -> 15 x 20 tiles; input tile rows 2ty-1 .. 2ty+2, cols 2tx-1 .. 2tx+2.
 // ---------------------------------------------------------------------------
 constexpr int kTilesY = 15, kTilesX = 20, kTilesPerImg = 300;
+// the transformed activations are pre-scaled by 2^8 before the (hi, lo) split so that the UNSCALED low
+// half stays a normal fp16 number for every |u| > 1e-3 (|u| <= 4 * 16 keeps hi < 65504)
+constexpr float kWinoActScale = 256.0f;
 
 // U[pos][n*300 + tile][ci] = (B^T d B)[pos]; one block per (image, tile), thread = 4 channels.
 __global__ void __launch_bounds__(128)
@@ -414,7 +424,7 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
         for (int j = 0; j < 4; ++j) {
             __half hh[4], hl[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_one(u[i][j][e], hh[e], hl[e]);
+            for (int e = 0; e < 4; ++e) split_one_unscaled(u[i][j][e] * kWinoActScale, hh[e], hl[e]);
             const int64_t off = ((int64_t)(i * 4 + j) * rows_pad + nt) * kE + c0;
             *reinterpret_cast<uint2 *>(u_hi + off) =
                 make_uint2((uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16),
@@ -942,19 +952,20 @@ extern "C" int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_strea
 }
 
 extern "C" int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
-                              int32_t transpose, float scale, spb_stream stream) {
+                              int32_t transpose, float scale, int32_t lo_unscaled, spb_stream stream) {
     SPB_CHECK_ARG(d_x && d_hi && d_lo, "null device pointer");
     SPB_CHECK_ARG(n_outer > 0 && C > 0 && HW > 0, "bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     if (transpose) {
         SPB_CHECK_ARG(n_outer <= 65535, "too many outer slices for one launch");
+        SPB_CHECK_ARG(lo_unscaled == 0, "lo_unscaled is only supported without transpose");
         dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n_outer);
         split_transpose_kernel<<<grid, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, C, HW, scale);
     } else {
         const int64_t total = n_outer * C * HW;
         int64_t blocks = (total + 255) / 256;
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale);
+        split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale, lo_unscaled);
     }
     SPB_LAUNCH_CHECK();
     return SPB_OK;
@@ -1000,7 +1011,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
     prof_begin(kTagPrep, s);
-    SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, stream));
+    SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, 0, stream));
     vfmean_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(io->d_vf, ws.vfmean, N);
     SPB_LAUNCH_CHECK();
     prof_end(s);
@@ -1057,7 +1068,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                 prof_end(s);
                 prof_begin(kTagConvH, s);
                 ConvGemmArgs a{ws.u_hi, ws.u_lo, (const __half *)w->ww_hi, (const __half *)w->ww_lo, w->d_wino_row_base,
-                               16 * (int64_t)kGateCols, nullptr, ws.wm, kGateCols, 16, kGateCols, 1, w->inv_scale_w};
+                               16 * (int64_t)kGateCols, nullptr, ws.wm, kGateCols, 16, kGateCols, 1, w->inv_scale_w / kWinoActScale};
                 a.rows_per_img = (int)ws.rows_pad;
                 SPB_TRY(conv_gemm_tc(a, s));
                 prof_end(s);

@@ -12,7 +12,7 @@ def run(ks, n_images, cols, use_tc, relu_a=False, reps=1):
     if relu_a: a = a.clamp_min(0)
     w = torch.randn(cols, ks, ks, 512, generator=g, device=dev) * 0.02
     a_hi = torch.empty_like(a, dtype=torch.float16); a_lo = torch.empty_like(a_hi)
-    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0, _lib.current_stream()))
+    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0, 0, _lib.current_stream()))
     w_hi, w_lo, inv = split_pair(w.reshape(cols, -1))
     out = torch.empty((n_images * 1200, cols), device=dev)
     def call():

@@ -32,9 +32,10 @@ def test_batched_gemm_mode_ks1(lib):
     a = torch.randn(B, 1200, 512, generator=g, device=dev)
     w = torch.randn(B * cols, 512, generator=g, device=dev) * 0.05
     a_hi = torch.empty_like(a, dtype=torch.float16); a_lo = torch.empty_like(a_hi)
-    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0,
+    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 256.0, 1,
                                   _lib.current_stream()), "split")
-    w_hi, w_lo, inv = split_pair(w)
+    w_hi, w_lo, inv = split_pair(w, lo_unscaled=True)
+    inv = inv / 256.0
     base = (torch.arange(B, device=dev, dtype=torch.int32) * cols).contiguous()
     out = torch.empty((B * 1200, cols), device=dev)
     _lib.check(lib.spb_conv_gemm(_lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(base),
@@ -42,7 +43,9 @@ def test_batched_gemm_mode_ks1(lib):
                "spb_conv_gemm")
     ref = torch.einsum("brk,bck->brc", a.double(), w.double().view(B, cols, 512)).reshape(B * 1200, cols)
     err = (out.double() - ref).abs().max().item()
-    assert err < 2e-6 * ref.abs().max().item(), err
+    # one accumulator takes all 3 x 32 products of a K = 512 tile: the tensor core's truncating adds
+    # leave ~1.5e-6 relative (the two-accumulator conv kernel: 6e-7)
+    assert err < 5e-6 * ref.abs().max().item(), err
 
 
 def _conv_case(lib, ks, n_images, cols, use_tc, per_image_sets=0, seed=0):
@@ -56,7 +59,7 @@ def _conv_case(lib, ks, n_images, cols, use_tc, per_image_sets=0, seed=0):
     w = torch.randn(rows, ks, ks, 512, generator=g, device=dev) * 0.02
     bias = torch.randn(rows, generator=g, device=dev)
     a_hi = torch.empty_like(a, dtype=torch.float16); a_lo = torch.empty_like(a_hi)
-    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0,
+    _lib.check(lib.spb_split_fp16(_lib.ptr(a), _lib.ptr(a_hi), _lib.ptr(a_lo), a.numel(), 1, 1, 0, 1.0, 0,
                                   _lib.current_stream()), "split")
     # the device split equals the host one
     hi_ref = a.double().to(torch.float16)
