@@ -244,7 +244,9 @@ int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t
 int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream);
 
 /* One implicit-GEMM convolution on its own (unit tests / profiling of the hot kernel):
- * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]. */
+ * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]  (ks = 3, 5; operand pairs
+ * hi + lo/2^11).  ks = 1 is the batched GEMM of the Winograd path (tensor cores only, operand pairs with an
+ * unscaled low half) and writes tile-major: d_out[((n*cols/128 + col/128)*1200 + p)*128 + col%128]. */
 int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, const void *d_w_lo,
                   const int32_t *d_w_row_base, int64_t w_rows, const float *d_bias, float *d_out, int64_t ldo,
                   int32_t n_images, int32_t cols, int32_t ks, float inv_scale, int32_t use_tensor_cores,

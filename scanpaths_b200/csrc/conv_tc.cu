@@ -521,7 +521,9 @@ gemm_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             // group, no cross-warp barrier); the 10 GB of per-position results stream through L2 once,
             // so they are marked evict-first to keep the weights and activation rows resident
             const uint32_t stage_out = out_smem + (uint32_t)(warp - 2) * (kOutRows * 32 * 4);
-            const int64_t row0 = (int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix;
+            // tile-major result layout [batch][channel tile][row][128]: every tile writes ONE contiguous 120 KB
+            // block (sequential DRAM bursts) instead of 240 512-byte pieces 8 KB apart
+            const int64_t row0 = ((int64_t)img * nct + c_tile) * rows_per_img + p_tile * kTilePix + half * kHalfPix;
 #pragma unroll
             for (int rr = 0; rr < kHalfPix / kOutRows; ++rr) {
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -536,7 +538,7 @@ gemm_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 if (lane == 0) {
                     asm volatile(
                         "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-                        ::"l"(&tmOut), "r"(stage_out), "r"(c_tile * kTileCh + q * 32), "r"((int)(row0 + rr * kOutRows)),
+                        ::"l"(&tmOut), "r"(stage_out), "r"(q * 32), "r"((int)(row0 + rr * kOutRows)),
                           "l"(evict_first)
                         : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -608,7 +610,8 @@ static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, i
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
     // ks = 3 / 5: convolution over 30 x 40 images (rows_per_img = 1200), operand pairs x = hi + lo / 2^11.
-    // ks = 1: plain batched GEMM (gemm_tc_flat_kernel), operand pairs with UNSCALED low half x = hi + lo;
+    // ks = 1: plain batched GEMM (gemm_tc_flat_kernel), operand pairs with UNSCALED low half x = hi + lo,
+    // result written TILE-MAJOR: out[((b * cols/128 + col/128) * rows_per_img + row) * 128 + col % 128] (ldo unused);
     // out[b][row][col] = sum_k a[b][row][k] w[w_row_base[b] + col][k] with rows_per_img rows per batch
     // entry (the per-position GEMMs of the Winograd path).
     const int rows = a.ks == 1 ? a.rows_per_img : kHW;
@@ -627,7 +630,8 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
-    if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, a.ks == 1 ? 32 : kTileCh);
+    if (!rc) rc = a.ks == 1 ? make_map_out(&mo, a.out, kTileCh, (int64_t)a.n_images * (a.cols / kTileCh) * rows, 32)
+                            : make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, kTileCh);
     if (rc) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;

@@ -471,7 +471,7 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
             float m[16];
 #pragma unroll
             for (int pos = 0; pos < 16; ++pos)
-                m[pos] = M ? M[((int64_t)pos * rows_pad + row) * kGateCols + gc + g * 32] : 0.0f;
+                m[pos] = M ? M[(((int64_t)pos * (kGateCols / 128) + (gc >> 7)) * rows_pad + row) * 128 + (gc & 127) + g * 32] : 0.0f;
             float t[4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -888,7 +888,7 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 // ---------------------------------------------------------------------------
 struct Workspace {
     __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2], *u_hi, *u_lo;
-    float *wm;             // Winograd per-position GEMM results [16][rows_pad][2048]
+    float *wm;             // Winograd per-position GEMM results, tile-major [16][2048/128][rows_pad][128]
     int64_t rows_pad;
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
