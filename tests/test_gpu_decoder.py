@@ -174,3 +174,30 @@ def test_decode_waves_and_module_api(lib, golden_dir):
     ref = g["f64_all_actions_prob"][:2, :4]
     rel = np.abs(a["all_actions_prob"][:2].cpu().numpy() - ref) / ref
     assert rel.max() < RTOL
+
+
+@pytest.mark.parametrize("seed,scale", [(11, 1.0), (12, 4.0), (13, 0.25)])
+def test_decode_other_seeds_and_feature_scales(lib, seed, scale):
+    """Seeds without a recorded golden, and feature maps 4x larger / smaller than the calibrated
+    synthetic ones (exercises the operand scaling): every route against the float64 oracle run here
+    on the host (8 steps, 1 image).  With 4x features the logits reach ~5 and the float32 reference
+    itself drifts to ~5e-6 by step 8, so there the bound is relative to the reference's own error."""
+    from oracle import decoder as OD
+    from scanpaths_b200.models.baseline_attention import CudaDecoder
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    dev = torch.device("cuda")
+    T = 8
+    sd = random_state_dict("OSIE", seed, calibrated=True, bias_std=0.05)
+    vf = synthetic_features(1, seed) * scale
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        p64 = OD.decode(sd, vf.double(), "OSIE", steps=T)["all_actions_prob"].numpy()
+        p32 = OD.decode(sd, vf.float(), "OSIE", steps=T)["all_actions_prob"].double().numpy()
+    ref_err = float((np.abs(p32 - p64) / p64).max())
+    bound = max(RTOL, 3.0 * ref_err) if scale > 1 else RTOL
+    for mode in (2, 1):                      # tcgen05 direct, tcgen05 Winograd (product path)
+        dec = CudaDecoder(sd, "OSIE", T, dev, wave=1, use_tensor_cores=mode)
+        probs, _, _, _ = dec.decode(vf.to(dev))
+        err = float((np.abs(probs[0].double().cpu().numpy() - p64) / p64).max())
+        print("seed %d scale %.2f mode %d: %.2e (float32 reference: %.2e)" % (seed, scale, mode, err, ref_err))
+        assert err < bound, (mode, err, ref_err)
