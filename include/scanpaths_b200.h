@@ -243,20 +243,25 @@ typedef struct spb_decoder_io {
 int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t n_heads, int32_t steps);
 int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream);
 
-/* One implicit-GEMM convolution on its own (unit tests / profiling of the hot kernel):
+/* One implicit-GEMM convolution on its own (unit tests / profiling of the kernel):
  * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]  (ks = 3, 5; operand pairs
- * hi + lo/2^11).  ks = 1 is the batched GEMM of the Winograd path (tensor cores only, operand pairs with an
- * unscaled low half) and writes tile-major: d_out[((n*cols/128 + col/128)*1200 + p)*128 + col%128]. */
+ * x = hi + lo/2^11, a NHWC [N,30,40,512], w [rows, ks*ks*512]). */
 int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, const void *d_w_lo,
                   const int32_t *d_w_row_base, int64_t w_rows, const float *d_bias, float *d_out, int64_t ldo,
                   int32_t n_images, int32_t cols, int32_t ks, float inv_scale, int32_t use_tensor_cores,
                   spb_stream stream);
 
-/* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11 (lo_unscaled = 0, operands of the ks = 3 / 5
- * convolutions) or x*scale = hi + lo (lo_unscaled = 1, operands of the ks = 1 batched GEMM; the caller
- * picks `scale` so that lo stays a normal fp16).  NCHW [N,C,HW] -> NHWC when `transpose`. */
+/* The Winograd F(2x4,3x3) gate GEMMs of the product path on their own (unit tests / profiling), position
+ * p = 4j + i with i = 0..3 the row position (F(2,3)) and j = 0..5 the column position (F(4,3)):
+ *   m[i][j] = u[p] . w[p]^T  (K = 512),  out[2j] = m[0][j]+m[1][j]+m[2][j],  out[2j+1] = m[1][j]-m[2][j]-m[3][j]
+ * d_u  [24][rows_pad][512], d_w [24*cols][512]: fp16 pairs x = hi + lo/2^11; rows_pad, cols % 128 == 0;
+ * d_out[((k*cols/128 + col/128)*rows_pad + row)*128 + col%128], k = 0..11, scaled by inv_scale. */
+int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
+                  int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream);
+
+/* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11.  NCHW [N,C,HW] -> NHWC when `transpose`. */
 int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
-                   int32_t transpose, float scale, int32_t lo_unscaled, spb_stream stream);
+                   int32_t transpose, float scale, spb_stream stream);
 
 #ifdef __cplusplus
 }

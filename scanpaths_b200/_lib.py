@@ -83,8 +83,9 @@ SYMBOLS.update({
     "spb_decode": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderIO), C.c_void_p]),
     "spb_conv_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                                    C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "spb_wino_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "spb_split_fp16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                 C.c_float, C.c_int32, C.c_void_p]),
+                                 C.c_float, C.c_void_p]),
 })
 
 _lib = None

@@ -102,15 +102,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cf. cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups |
 // version 1 | layout SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((8 * kSwizzleBytes) >> 4) << 32;
+    d |= (uint64_t)((8 * SWIZZLE_BYTES) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(kSwizzleBytes == 128 ? 2 : 4) << 61;
+    d |= (uint64_t)(SWIZZLE_BYTES == 128 ? 2 : 4) << 61;
     return d;
 }
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) { return umma_desc_kmajor<kSwizzleBytes>(saddr); }
 
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128 (channels), N = 240 (pixels)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTilePix >> 3) << 17) | ((uint32_t)(kTileCh >> 4) << 24);
@@ -392,44 +394,82 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 }
 
 // ---------------------------------------------------------------------------
-// Flat batched GEMM for the Winograd path (ks = 1): out[b][row][col] = sum_k a[b][row][k] w[base_b + col][k],
-// K = 512.  Same tile (128 channels x 240 rows), same TMA / UMMA staging, but:
-//   * K is only 32 k-steps, so one TMEM accumulator per tile is safe (no mid-K drain), and the
-//     operand pairs use an UNSCALED low half (x*s = hi + lo, see spb_split_fp16 lo_unscaled): all three
-//     products hi*hi + hi*lo + lo*hi accumulate into the SAME accumulator;
-//   * that leaves room for TWO accumulators (2 x 240 of the 512 TMEM columns): the drain warps read
-//     tile i (TMEM -> registers costs ~2k cycles per accumulator at 64 B/clk) and run its epilogue
-//     while the tensor core already works on tile i+1.  With the two-accumulator scheme of the
-//     convolution kernel the drains of these short tiles left the tensor pipe idle 33 % of the time.
-//   * measured (B200): 5.7 ms per 256 images and step; 4.6 ms (the MMA bound) with the stores disabled --
-//     what is left is the cost of streaming 10 GB of per-position results to HBM, whatever the store
-//     mechanism (plain st.global, 15 KB TMA boxes per half, 3.8 KB boxes per warp: all within 3 %).
+// Winograd F(2x4, 3x3) gate GEMMs with the ROW half of the output transform in the epilogue.
+//   m[i][j] = U[4j+i] . W[4j+i]^T     (K = 512; i = 0..3 the F(2,3) row position, j = 0..5 the F(4,3) column position)
+//   out[2j + 0] = m[0][j] + m[1][j] + m[2][j]
+//   out[2j + 1] = m[1][j] - m[2][j] - m[3][j]          (= A_2^T m; the cell kernel finishes with . A_4)
+// 24 multiplies per 8 outputs (the direct convolution: 72, F(2x2): 32), and only 12 result planes leave the
+// SM (and are read back by the cell kernel) instead of 24.
+//   * tile = 128 gate columns (UMMA M) x 128 Winograd tiles (UMMA N) x the 4 row positions of one j; the K
+//     loops of the 4 positions run back to back.  Operands are (hi, lo) fp16 pairs, x = hi + lo / 2^11, and
+//     every position has TWO 128-column TMEM accumulators side by side: main = hi*hi, corr = hi*lo + lo*hi.
+//     Per k-step ONE N = 256 MMA  W_hi x [X_hi ; X_lo] -> [main | corr]  (the two activation operand tiles are
+//     adjacent in shared memory) and one N = 128 MMA  W_lo x X_hi -> corr.  The truncating adds of the tensor
+//     core then act on 32 (main) and 64 (corr, weight 2^-11) accumulation steps instead of 96;
+//   * two position buffers (2 x 256 = all 512 TMEM columns): the tensor core works on position p+1 while the
+//     drain warps read position p (thread = 1 gate column x 64 tiles), fold main + corr / 2^11 into two running
+//     sums in registers (fp32, round-to-nearest) and release the buffer; after i = 3 the two sums are stored
+//     (a warp store = 32 adjacent gate columns of one tile row, evict-first: the results stream through L2 once);
+//   * 64 KB stages {W_hi, W_lo, X_hi, X_lo} x 128 rows x 64 k, 128-byte swizzle, 3-deep mbarrier ring.
+// Measured (B200, 256 images): the MMA thread spends ~85 % of the kernel blocked on MMA issue and the chip runs
+// at its power cap (~1.4 GHz): the issued rate is 0.85-0.9 of what cuBLAS bf16 sustains on the same box.  A CTA-pair
+// (cta_group::2) variant that halves the shared-memory operand traffic was built, verified and timed: same
+// duration -- the bound is the number of issued MMA flops, which is why this is F(2x4) and not F(2x2).
+// Result layout (tile-major): out[((2j + r) * cols/128 + col/128) * rows_pad + row][col % 128].
 // ---------------------------------------------------------------------------
+namespace wg {
+constexpr int kTileRows = 128;                             // Winograd tiles per GEMM tile (UMMA N)
+constexpr int kPosI = 4, kPosJ = 6;                        // F(2,3) positions folded in the epilogue, F(4,3) positions
+constexpr int kBK = 64;                                    // k-block: 64 fp16 = one 128-byte swizzle row
+constexpr int kOpBytes = 128 * kBK * 2;                    // 16 KB per operand tile
+constexpr int kStageBytes = 4 * kOpBytes;                  // 64 KB: W_hi, W_lo, X_hi, X_lo
+constexpr int kStages = 3;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kAccCols = 128, kNumBuf = 2;                 // per buffer: main | corr
+constexpr uint32_t kIdescN256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kTileCh >> 4) << 24);
+constexpr uint32_t kIdescN128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kTileCh >> 4) << 24);
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+}  // namespace wg
+
+__device__ __forceinline__ void umma_f16_idesc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_constant__ CUtensorMap tmU_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                    const __grid_constant__ CUtensorMap tmOut, ConvGemmArgs a, int num_tiles, int nct, int kPT,
-                    int rows_per_img) {
+                    float *__restrict__ out, int num_tiles, int nct, int ntb, int cols, int64_t rows_pad,
+                    float inv_scale) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar0 = base + kStages * kStageBytes;
+    const uint32_t bar0 = base + wg::kStages * wg::kStageBytes;
     auto full_bar = [&](int s) { return bar0 + 8 * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8 * (kStages + s); };
-    auto acc_full_bar = [&](int b) { return bar0 + 8 * (2 * kStages + b); };        // MMA -> drain warps
-    auto acc_empty_bar = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };   // drain warps -> MMA
-    const uint32_t tmem_slot = bar0 + 8 * (2 * kStages + 4);
-    const uint32_t out_smem = bar0 + 256;
+    auto empty_bar = [&](int s) { return bar0 + 8 * (wg::kStages + s); };
+    auto acc_full_bar = [&](int b) { return bar0 + 8 * (2 * wg::kStages + b); };                   // MMA -> drain warps
+    auto acc_empty_bar = [&](int b) { return bar0 + 8 * (2 * wg::kStages + wg::kNumBuf + b); };    // drain warps -> MMA
+    const uint32_t tmem_slot = bar0 + 8 * (2 * wg::kStages + 2 * wg::kNumBuf);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kNumKB = kE / kBlockK;
+    constexpr int kNumKB = kE / wg::kBK;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
+        for (int s = 0; s < wg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < wg::kNumBuf; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -443,109 +483,108 @@ gemm_tc_flat_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+    // tile -> (column tile fastest, then row block, then j): the 16 column tiles of one row block run at the
+    // same time (its U rows come from HBM once), the weights of one j (16 MB) stay in L2
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
-                const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
-                const int y0 = p_tile * (kTilePix / kW);
-                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-                    const uint32_t sa = base + s * kStageBytes;
-                    mbar_expect_tx(full_bar(s), kStageBytes);
-                    tma_load_2d(sa, &tmW_hi, full_bar(s), kb * kBlockK, row_base);
-                    tma_load_2d(sa + kWBytes, &tmW_lo, full_bar(s), kb * kBlockK, row_base);
-                    tma_load_4d(sa + 2 * kWBytes, &tmA_hi, full_bar(s), kb * kBlockK, 0, y0, img);
-                    tma_load_4d(sa + 2 * kWBytes + kActBytes, &tmA_lo, full_bar(s), kb * kBlockK, 0, y0, img);
+                const int c_tile = tile % nct, tb = (tile / nct) % ntb, j = tile / (nct * ntb);
+                for (int i = 0; i < wg::kPosI; ++i) {
+                    const int pos = j * wg::kPosI + i;
+                    const int w_row = pos * cols + c_tile * kTileCh;
+                    for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                        const int s = it % wg::kStages;
+                        mbar_wait(empty_bar(s), ((it / wg::kStages) & 1) ^ 1);
+                        const uint32_t sa = base + s * wg::kStageBytes;
+                        mbar_expect_tx(full_bar(s), wg::kStageBytes);
+                        tma_load_2d(sa, &tmW_hi, full_bar(s), kb * wg::kBK, w_row);
+                        tma_load_2d(sa + wg::kOpBytes, &tmW_lo, full_bar(s), kb * wg::kBK, w_row);
+                        tma_load_3d(sa + 2 * wg::kOpBytes, &tmU_hi, full_bar(s), kb * wg::kBK, tb * wg::kTileRows, pos);
+                        tma_load_3d(sa + 3 * wg::kOpBytes, &tmU_lo, full_bar(s), kb * wg::kBK, tb * wg::kTileRows, pos);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-                const int buf = ti & 1;
-                const uint32_t d_acc = tmem_base + buf * kCorrCol;
-                mbar_wait(acc_empty_bar(buf), ((ti >> 1) & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < kNumKB; ++kb, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(full_bar(s), (it / kStages) & 1);
+            uint32_t it = 0, pc = 0;                       // pc: positions issued so far (buffer ring index)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int i = 0; i < wg::kPosI; ++i, ++pc) {
+                    const int buf = pc & (wg::kNumBuf - 1);
+                    const uint32_t d_main = tmem_base + buf * 2 * wg::kAccCols, d_corr = d_main + wg::kAccCols;
+                    mbar_wait(acc_empty_bar(buf), ((pc / wg::kNumBuf) & 1) ^ 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = base + s * kStageBytes;
-                    const uint64_t w_hi = umma_desc_sw128(sa), w_lo = umma_desc_sw128(sa + kWBytes);
-                    const uint64_t x_hi = umma_desc_sw128(sa + 2 * kWBytes), x_lo = umma_desc_sw128(sa + 2 * kWBytes + kActBytes);
+                    for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                        const int s = it % wg::kStages;
+                        mbar_wait(full_bar(s), (it / wg::kStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = base + s * wg::kStageBytes;
+                        const uint64_t w_hi = umma_desc_kmajor<128>(sa), w_lo = umma_desc_kmajor<128>(sa + wg::kOpBytes);
+                        const uint64_t x_hilo = umma_desc_kmajor<128>(sa + 2 * wg::kOpBytes);   // 256 rows: X_hi then X_lo
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                        // small terms first, then the leading product
-                        umma_f16(d_acc, w_hi + adv, x_lo + adv, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_f16(d_acc, w_lo + adv, x_hi + adv, 1u);
-                        umma_f16(d_acc, w_hi + adv, x_hi + adv, 1u);
+                        for (int k = 0; k < wg::kBK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                            // [main | corr] (+)= W_hi . [X_hi ; X_lo]^T, then corr += W_lo . X_hi^T
+                            umma_f16_idesc(d_main, w_hi + adv, x_hilo + adv, wg::kIdescN256, acc);
+                            umma_f16_idesc(d_corr, w_lo + adv, x_hilo + adv, wg::kIdescN128, 1u);
+                        }
+                        umma_commit(empty_bar(s));
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit(acc_full_bar(buf));
                 }
-                umma_commit(acc_full_bar(buf));
             }
         }
     } else {
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const int r = q * 32 + lane;
+        const int q = warp & 3, half = (warp - 2) >> 2;    // TMEM lane quarter (gate columns), half of the 128 tiles
+        constexpr int kMine = wg::kTileRows / 2;           // 64 tiles per thread
         uint64_t evict_first;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
-        uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-            const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
-            const int buf = ti & 1;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kCorrCol + half * kHalfPix;
-            float tot[kHalfPix];
-            mbar_wait(acc_full_bar(buf), (ti >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t pc = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int c_tile = tile % nct, tb = (tile / nct) % ntb, j = tile / (nct * ntb);
+            float sa[kMine], sb[kMine];
 #pragma unroll
-            for (int c = 0; c < kHalfPix; c += 8) {
-                uint32_t v[8];
-                tmem_ld8(lane_addr + c, v);
+            for (int i = 0; i < wg::kPosI; ++i, ++pc) {
+                const int buf = pc & (wg::kNumBuf - 1);
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * wg::kAccCols + half * kMine;
+                mbar_wait(acc_full_bar(buf), (pc / wg::kNumBuf) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tot[c + j] = __uint_as_float(v[j]);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_bar(buf)) : "memory");
-
-            const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
-            const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
-            // every drain warp stores its own 32-channel x 30-pixel boxes (own staging slice, own bulk
-            // group, no cross-warp barrier); the 10 GB of per-position results stream through L2 once,
-            // so they are marked evict-first to keep the weights and activation rows resident
-            const uint32_t stage_out = out_smem + (uint32_t)(warp - 2) * (kOutRows * 32 * 4);
-            // tile-major result layout [batch][channel tile][row][128]: every tile writes ONE contiguous 120 KB
-            // block (sequential DRAM bursts) instead of 240 512-byte pieces 8 KB apart
-            const int64_t row0 = ((int64_t)img * nct + c_tile) * rows_per_img + p_tile * kTilePix + half * kHalfPix;
+                for (int c = 0; c < kMine; c += 16) {
+                    uint32_t vm[2][8], vc[2][8];
 #pragma unroll
-            for (int rr = 0; rr < kHalfPix / kOutRows; ++rr) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
+                    for (int b = 0; b < 2; ++b) {
+                        tmem_ld8(lane_addr + c + 8 * b, vm[b]);
+                        tmem_ld8(lane_addr + wg::kAccCols + c + 8 * b, vc[b]);
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < kOutRows; ++j) {
-                    const float v = tot[rr * kOutRows + j] * a.inv_scale + bias;
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_out + (uint32_t)(j * 32 + lane) * 4), "f"(v) : "memory");
+                    for (int e = 0; e < 16; ++e) {
+                        const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, __uint_as_float(vm[e >> 3][e & 7]));
+                        if (i == 0) sa[c + e] = m;
+                        else if (i == 1) { sa[c + e] += m; sb[c + e] = m; }
+                        else if (i == 2) { sa[c + e] += m; sb[c + e] -= m; }
+                        else sb[c + e] -= m;
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
-                    asm volatile(
-                        "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-                        ::"l"(&tmOut), "r"(stage_out), "r"(q * 32), "r"((int)(row0 + rr * kOutRows)),
-                          "l"(evict_first)
-                        : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_bar(buf)) : "memory");
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t row0 = ((int64_t)(2 * j + r) * nct + c_tile) * rows_pad + (int64_t)tb * wg::kTileRows + half * kMine;
+                float *dst = out + row0 * kTileCh + q * 32 + lane;
+#pragma unroll
+                for (int e = 0; e < kMine; ++e) {
+                    const float v = (r == 0 ? sa[e] : sb[e]) * inv_scale;
+                    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(dst + (int64_t)e * kTileCh), "f"(v), "l"(evict_first)
+                                 : "memory");
                 }
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -583,13 +622,13 @@ static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images, int rows_
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K) {
+static int make_map_b(CUtensorMap *m, const __half *ptr, int64_t rows, int64_t K, int block_k = kBlockK) {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileCh};
+    const cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)kTileCh};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, kSwizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -609,15 +648,9 @@ static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, i
 
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
-    // ks = 3 / 5: convolution over 30 x 40 images (rows_per_img = 1200), operand pairs x = hi + lo / 2^11.
-    // ks = 1: plain batched GEMM (gemm_tc_flat_kernel), operand pairs with UNSCALED low half x = hi + lo,
-    // result written TILE-MAJOR: out[((b * cols/128 + col/128) * rows_per_img + row) * 128 + col % 128] (ldo unused);
-    // out[b][row][col] = sum_k a[b][row][k] w[w_row_base[b] + col][k] with rows_per_img rows per batch
-    // entry (the per-position GEMMs of the Winograd path).
-    const int rows = a.ks == 1 ? a.rows_per_img : kHW;
-    if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || rows <= 0 || rows % kTilePix != 0 ||
-        a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0) {
-        set_error("conv_gemm_tc: cols must be a multiple of %d, rows per image of %d, ks 1, 3 or 5", kTileCh, kTilePix);
+    // ks = 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11
+    if (a.cols % kTileCh != 0 || (a.ks != 3 && a.ks != 5) || a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0) {
+        set_error("conv_gemm_tc: cols must be a multiple of %d, ks 3 or 5, out 16-byte aligned", kTileCh);
         return SPB_ERR_ARG;
     }
     if (get_encode() == nullptr) {
@@ -626,17 +659,16 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     }
     const int64_t K = (int64_t)a.ks * a.ks * kE;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo;
-    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows);
-    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
+    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, kHW);
+    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, kHW);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
-    if (!rc) rc = a.ks == 1 ? make_map_out(&mo, a.out, kTileCh, (int64_t)a.n_images * (a.cols / kTileCh) * rows, 32)
-                            : make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, kTileCh);
+    if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * kHW, kTileCh);
     if (rc) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
     }
-    const int nct = a.cols / kTileCh, pt = rows / kTilePix;
+    const int nct = a.cols / kTileCh, pt = kHW / kTilePix;
     const int64_t tiles64 = (int64_t)nct * pt * a.n_images;
     if (tiles64 > 0x7fffffff) {
         set_error("conv_gemm_tc: too many tiles");
@@ -646,13 +678,59 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
 #define SPB_LAUNCH_TC(KS_)                                                                                          \
     SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
-    if (a.ks == 1) {
-        SPB_CUDA(cudaFuncSetAttribute(gemm_tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        gemm_tc_flat_kernel<<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows);
-    } else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
+    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, kHW)
+    if (a.ks == 3) { SPB_LAUNCH_TC(3); }
     else { SPB_LAUNCH_TC(5); }
 #undef SPB_LAUNCH_TC
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
+// Winograd F(2x4,3x3) gate GEMMs + row output transform (wino_gemm_tc_kernel).
+//   u  [24][rows_pad][512] fp16 pairs (hi + lo/2^11), position p = 4j + i;  w [24 * cols][512] fp16 pairs;
+//   out [12][cols/128][rows_pad][128] fp32.  rows_pad % 128 == 0, cols % 128 == 0.
+int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s) {
+    using namespace tc;
+    constexpr int kPos = wg::kPosI * wg::kPosJ;
+    if (rows_pad <= 0 || rows_pad % wg::kTileRows != 0 || cols <= 0 || cols % kTileCh != 0 || ((uintptr_t)out & 15) != 0) {
+        set_error("wino_gemm_tc: rows_pad must be a multiple of %d, cols of %d", wg::kTileRows, kTileCh);
+        return SPB_ERR_ARG;
+    }
+    if (get_encode() == nullptr) {
+        set_error("wino_gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+        return SPB_ERR_CUDA;
+    }
+    const int nct = cols / kTileCh;
+    const int64_t ntb = rows_pad / wg::kTileRows;
+    if ((int64_t)kPos * rows_pad > 0x7fffffff || wg::kPosJ * nct * ntb > 0x7fffffff) {
+        set_error("wino_gemm_tc: too many rows");
+        return SPB_ERR_ARG;
+    }
+    CUtensorMap mu_hi, mu_lo, mw_hi, mw_lo;
+    auto make_u = [&](CUtensorMap *m, const __half *ptr) -> int {
+        const cuuint64_t dims[3] = {(cuuint64_t)kE, (cuuint64_t)rows_pad, (cuuint64_t)kPos};
+        const cuuint64_t strides[2] = {(cuuint64_t)kE * 2, (cuuint64_t)rows_pad * kE * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)wg::kBK, (cuuint32_t)wg::kTileRows, 1};
+        const cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *)ptr, dims, strides, box, es,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS ? 0 : (int)r;
+    };
+    int rc = make_u(&mu_hi, u_hi);
+    if (!rc) rc = make_u(&mu_lo, u_lo);
+    if (!rc) rc = make_map_b(&mw_hi, w_hi, (int64_t)kPos * cols, kE, wg::kBK);
+    if (!rc) rc = make_map_b(&mw_lo, w_lo, (int64_t)kPos * cols, kE, wg::kBK);
+    if (rc) {
+        set_error("wino_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
+        return SPB_ERR_CUDA;
+    }
+    const int num_tiles = (int)(wg::kPosJ * nct * ntb);
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
+    wino_gemm_tc_kernel<<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb, cols,
+                                                              rows_pad, inv_scale);
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }

@@ -76,19 +76,12 @@ split_transpose_kernel(const float *__restrict__ x, __half *__restrict__ hi, __h
     }
 }
 
-// unscaled low half: v = hi + lo (used where the caller pre-scales v so that lo stays a normal fp16)
-__device__ __forceinline__ void split_one_unscaled(float v, __half &hi, __half &lo) {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
-}
-
 __global__ void __launch_bounds__(256)
 split_plain_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int64_t total,
-                   float scale, int lo_unscaled) {
+                   float scale) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         __half h, l;
-        if (lo_unscaled) split_one_unscaled(x[i] * scale, h, l);
-        else split_one(x[i] * scale, h, l);
+        split_one(x[i] * scale, h, l);
         hi[i] = h; lo[i] = l;
     }
 }
@@ -363,69 +356,75 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// Winograd F(2x2, 3x3) for the 3x3 gate convolution of h (product path).
-//   Y = A^T [ (G g G^T) (.) (B^T d B) ] A   per 2x2 output tile and (ci, co) pair, summed over ci:
-//   16 multiplies per 4 outputs instead of 36 -> 2.25x fewer tensor-core MMAs.  The per-position
-//   sums over ci are 16 independent GEMMs [tiles x 512] x [512 x 2048] (conv_tc.cu, ks = 1); the
-//   input transform (adds only) runs here in fp32 on the exact 22-bit h values and is re-split into
-//   fp16 pairs, the weight transform is done once in float64 (prepare_weights), and the output
-//   transform is folded into the cell kernel below.  Emulated end to end, the representation error
-//   of this path is 1.4e-7 rms on the convolution -- far inside the parity gate.
-// Tiles: image 30 x 40 -> 15 x 20 tiles; input tile rows 2ty-1 .. 2ty+2, cols 2tx-1 .. 2tx+2.
+// Winograd F(2x4, 3x3) for the 3x3 gate convolution of h (product path): output tiles of 2 rows x 4 columns.
+//   Y = A2^T [ (G2 g G4^T) (.) (B2^T d B4) ] A4   per tile and (ci, co) pair, summed over ci:
+//   24 multiplies per 8 outputs instead of 72 -> 3x fewer tensor-core MMAs (F(2x2): 2.25x).  The bound of the
+//   gate GEMMs is the number of issued MMA flops (the chip runs at its power cap), so this is what buys time.
+//   The per-position sums over ci are 24 independent GEMMs [tiles x 512] x [512 x 2048] (conv_tc.cu); the
+//   input transform runs here in fp32 on the exact 22-bit h values (small-integer coefficients) and is re-split
+//   into fp16 pairs, the weight transform is done once in float64 (prepare_weights), the row half of the
+//   output transform (A2^T) in the GEMM epilogue and the column half (. A4) in the cell kernel below.
+//   Emulated end to end (truncating tensor-core accumulator included) the error of this path is 1.0e-6 rms of
+//   the convolution's rms -- the direct route: 0.9e-6, F(2x2) with one accumulator per position: 2.4e-6.
+// Tiles: image 30 x 40 -> 15 x 10 tiles; input patch rows 2ty-1 .. 2ty+2, cols 4tx-1 .. 4tx+4.
+// F(4,3) uses the points 0, +-1, +-2, inf:
+//   B4^T = [4 0 -5 0 1 0; 0 -4 -4 1 1 0; 0 4 -4 -1 1 0; 0 -2 -1 2 1 0; 0 2 -1 -2 1 0; 0 4 0 -5 0 1]
+//   A4^T = [1 1 1 1 1 0; 0 1 -1 2 -2 0; 0 1 1 4 4 0; 0 1 -1 8 -8 1]
 // ---------------------------------------------------------------------------
-constexpr int kTilesY = 15, kTilesX = 20, kTilesPerImg = 300;
-// the transformed activations are pre-scaled by 2^8 before the (hi, lo) split so that the UNSCALED low
-// half stays a normal fp16 number for every |u| > 1e-3 (|u| <= 4 * 16 keeps hi < 65504)
-constexpr float kWinoActScale = 256.0f;
+constexpr int kTilesY = 15, kTilesX = 10, kTilesPerImg = 150;
+constexpr int kWinoPos = 24;        // position p = 4j + i (i: F(2,3) row position, j: F(4,3) column position)
 
-// U[pos][n*300 + tile][ci] = (B^T d B)[pos]; one block per (image, tile), thread = 4 channels.
+// U[p][n*150 + tile][ci] = (B2^T d B4)[i][j]; one block per (image, tile), thread = 4 channels.
 __global__ void __launch_bounds__(128)
 wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, __half *__restrict__ u_hi,
                   __half *__restrict__ u_lo, int64_t rows_pad) {
-    const int64_t nt = blockIdx.x;                   // n*300 + tile
+    const int64_t nt = blockIdx.x;                   // n*150 + tile
     const int64_t n = nt / kTilesPerImg;
     const int tile = (int)(nt - n * kTilesPerImg);
     const int ty = tile / kTilesX, tx = tile - ty * kTilesX;
     const int c0 = threadIdx.x * 4;
-    float d[4][4][4];
+    // column by column of the 4 x 6 patch: B2^T on the 4 rows first, so that only u[4][6] stays live
+    float u[4][6][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 6; ++b) {
+        float d[4][4];
+        const int xx = 4 * tx - 1 + b;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int yy = 2 * ty - 1 + a, xx = 2 * tx - 1 + b;
+        for (int a = 0; a < 4; ++a) {
+            const int yy = 2 * ty - 1 + a;
             if (yy >= 0 && yy < kH && xx >= 0 && xx < kW) {
-                load_h4(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + c0, d[a][b]);
+                load_h4(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + c0, d[a]);
             } else {
-                d[a][b][0] = d[a][b][1] = d[a][b][2] = d[a][b][3] = 0.0f;
+                d[a][0] = d[a][1] = d[a][2] = d[a][3] = 0.0f;
             }
         }
-    // rows: B^T d  (r0 = d0 - d2, r1 = d1 + d2, r2 = d2 - d1, r3 = d1 - d3), then columns
-    float u[4][4][4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            u[0][b][e] = d[0][b][e] - d[2][b][e];
-            u[1][b][e] = d[1][b][e] + d[2][b][e];
-            u[2][b][e] = d[2][b][e] - d[1][b][e];
-            u[3][b][e] = d[1][b][e] - d[3][b][e];
+            u[0][b][e] = d[0][e] - d[2][e];
+            u[1][b][e] = d[1][e] + d[2][e];
+            u[2][b][e] = d[2][e] - d[1][e];
+            u[3][b][e] = d[1][e] - d[3][e];
         }
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+        float t[6][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float t0 = u[i][0][e] - u[i][2][e], t1 = u[i][1][e] + u[i][2][e];
-            const float t2 = u[i][2][e] - u[i][1][e], t3 = u[i][1][e] - u[i][3][e];
-            u[i][0][e] = t0; u[i][1][e] = t1; u[i][2][e] = t2; u[i][3][e] = t3;
+            const float d0 = u[i][0][e], d1 = u[i][1][e], d2 = u[i][2][e], d3 = u[i][3][e], d4 = u[i][4][e], d5 = u[i][5][e];
+            t[0][e] = fmaf(4.0f, d0, fmaf(-5.0f, d2, d4));
+            t[1][e] = fmaf(-4.0f, d1 + d2, d3 + d4);
+            t[2][e] = fmaf(4.0f, d1 - d2, d4 - d3);
+            t[3][e] = fmaf(2.0f, d3 - d1, d4 - d2);
+            t[4][e] = fmaf(2.0f, d1 - d3, d4 - d2);
+            t[5][e] = fmaf(4.0f, d1, fmaf(-5.0f, d3, d5));
         }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 6; ++j) {
             __half hh[4], hl[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_one_unscaled(u[i][j][e] * kWinoActScale, hh[e], hl[e]);
-            const int64_t off = ((int64_t)(i * 4 + j) * rows_pad + nt) * kE + c0;
+            for (int e = 0; e < 4; ++e) split_one(t[j][e], hh[e], hl[e]);
+            const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
             *reinterpret_cast<uint2 *>(u_hi + off) =
                 make_uint2((uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16),
                            (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16));
@@ -433,12 +432,13 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
                 make_uint2((uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16),
                            (uint32_t)__half_as_ushort(hl[2]) | ((uint32_t)__half_as_ushort(hl[3]) << 16));
         }
+    }
 }
 
-// ConvLSTM cell with the Winograd output transform folded in: block = (tile row ty, image, 128-channel
-// group), thread = channel, loop over the 20 tiles of the row; per tile and gate the 16 per-position
-// GEMM results m[pos] (coalesced 128-byte lines) give the 2x2 pre-activations A^T m A.
-// M == NULL means h = 0 (first step).  HBM: 16 x 8 KB (M) + 4 x 8 KB (xg) + c, h per tile.
+// ConvLSTM cell with the column half of the Winograd output transform folded in: block = (tile row ty, image,
+// 128-channel group), thread = channel, loop over the 10 tiles of the row; per tile and gate the 12 planes
+// t[r][j] = (A2^T m)[r][j] of the GEMM (coalesced 128-byte lines) give the 2 x 4 pre-activations t . A4.
+// M == NULL means h = 0 (first step).  HBM: 12 x 2 KB (M) + 8 x 8 KB (xg) + c, h per tile and 128 channels.
 template <int S>
 __global__ void __launch_bounds__(128)
 lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ xg,
@@ -464,30 +464,28 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
     __syncthreads();
     const int gc = gate_col(ch, 0);
     for (int tx = 0; tx < kTilesX; ++tx) {
-        float pre[4][4];                              // [gate][oy*2 + ox]
+        float pre[4][8];                              // [gate][oy*4 + ox]
         const int64_t row = n * kTilesPerImg + ty * kTilesX + tx;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            float m[16];
 #pragma unroll
-            for (int pos = 0; pos < 16; ++pos)
-                m[pos] = M ? M[(((int64_t)pos * (kGateCols / 128) + (gc >> 7)) * rows_pad + row) * 128 + (gc & 127) + g * 32] : 0.0f;
-            float t[4][2];
+            for (int r = 0; r < 2; ++r) {
+                float t[6];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                t[i][0] = (m[4 * i] + m[4 * i + 1]) + m[4 * i + 2];
-                t[i][1] = (m[4 * i + 1] - m[4 * i + 2]) - m[4 * i + 3];
-            }
-#pragma unroll
-            for (int ox = 0; ox < 2; ++ox) {
-                pre[g][ox] = (t[0][ox] + t[1][ox]) + t[2][ox];
-                pre[g][2 + ox] = (t[1][ox] - t[2][ox]) - t[3][ox];
+                for (int j = 0; j < 6; ++j)
+                    t[j] = M ? M[(((int64_t)(2 * j + r) * (kGateCols / 128) + (gc >> 7)) * rows_pad + row) * 128 + (gc & 127) + g * 32]
+                             : 0.0f;
+                const float s12 = t[1] + t[2], d12 = t[1] - t[2], s34 = t[3] + t[4], d34 = t[3] - t[4];
+                pre[g][4 * r + 0] = (t[0] + s12) + s34;
+                pre[g][4 * r + 1] = fmaf(2.0f, d34, d12);
+                pre[g][4 * r + 2] = fmaf(4.0f, s34, s12);
+                pre[g][4 * r + 3] = fmaf(8.0f, d34, d12) + t[5];
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int oy = q >> 1, ox = q & 1;
-            const int64_t pix = n * kHW + (2 * ty + oy) * kW + 2 * tx + ox;
+        for (int q = 0; q < 8; ++q) {
+            const int oy = q >> 2, ox = q & 3;
+            const int64_t pix = n * kHW + (2 * ty + oy) * kW + 4 * tx + ox;
             const float *xp = xg + pix * kGateCols + gc;
             float p0 = pre[0][q] + xp[0], p1 = pre[1][q] + xp[32], p2 = pre[2][q] + xp[64];
             const float p3 = pre[3][q] + xp[96];
@@ -497,7 +495,7 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
                 float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
 #pragma unroll
                 for (int t9 = 0; t9 < 9; ++t9) {
-                    const float sv = halo[st][oy + t9 / 3][2 * tx + ox + t9 % 3];
+                    const float sv = halo[st][oy + t9 / 3][4 * tx + ox + t9 % 3];
                     r0 = fmaf(v[st][0][t9], sv, r0);
                     r1 = fmaf(v[st][1][t9], sv, r1);
                     r2 = fmaf(v[st][2][t9], sv, r2);
@@ -888,7 +886,7 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 // ---------------------------------------------------------------------------
 struct Workspace {
     __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2], *u_hi, *u_lo;
-    float *wm;             // Winograd per-position GEMM results, tile-major [16][2048/128][rows_pad][128]
+    float *wm;             // Winograd GEMM results after the row transform, tile-major [12][2048/128][rows_pad][128]
     int64_t rows_pad;
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
@@ -930,10 +928,10 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.sp_mem = (float *)take(N * S * kHW * 4);
     w.se_mem = (float *)take(N * S * kE * 4);
     w.drt_pre = (float *)take(N * HD * 48 * 4);
-    w.rows_pad = (N * kTilesPerImg + 239) / 240 * 240;
-    w.u_hi = (__half *)take(16 * w.rows_pad * kE * 2);
-    w.u_lo = (__half *)take(16 * w.rows_pad * kE * 2);
-    w.wm = (float *)take(16 * w.rows_pad * (int64_t)kGateCols * 4);
+    w.rows_pad = (N * kTilesPerImg + 127) / 128 * 128;
+    w.u_hi = (__half *)take(kWinoPos * w.rows_pad * kE * 2);
+    w.u_lo = (__half *)take(kWinoPos * w.rows_pad * kE * 2);
+    w.wm = (float *)take((kWinoPos / 2) * w.rows_pad * (int64_t)kGateCols * 4);
     w.bytes = o;
     return w;
 }
@@ -952,20 +950,19 @@ extern "C" int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_strea
 }
 
 extern "C" int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
-                              int32_t transpose, float scale, int32_t lo_unscaled, spb_stream stream) {
+                              int32_t transpose, float scale, spb_stream stream) {
     SPB_CHECK_ARG(d_x && d_hi && d_lo, "null device pointer");
     SPB_CHECK_ARG(n_outer > 0 && C > 0 && HW > 0, "bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
     if (transpose) {
         SPB_CHECK_ARG(n_outer <= 65535, "too many outer slices for one launch");
-        SPB_CHECK_ARG(lo_unscaled == 0, "lo_unscaled is only supported without transpose");
         dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n_outer);
         split_transpose_kernel<<<grid, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, C, HW, scale);
     } else {
         const int64_t total = n_outer * C * HW;
         int64_t blocks = (total + 255) / 256;
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale, lo_unscaled);
+        split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale);
     }
     SPB_LAUNCH_CHECK();
     return SPB_OK;
@@ -976,12 +973,17 @@ extern "C" int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void 
                              int64_t ldo, int32_t n_images, int32_t cols, int32_t ks, float inv_scale,
                              int32_t use_tensor_cores, spb_stream stream) {
     SPB_CHECK_ARG(d_a_hi && d_a_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
-    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 1 || ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
-    SPB_CHECK_ARG(ks != 1 || use_tensor_cores != 0, "ks = 1 (batched GEMM, 1200 rows per entry) needs the tensor-core path");
+    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
     ConvGemmArgs a{(const __half *)d_a_hi, (const __half *)d_a_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
                    d_w_row_base, w_rows, d_bias, d_out, ldo, n_images, cols, ks, inv_scale};
-    a.rows_per_img = kHW;
     return conv_gemm(a, use_tensor_cores != 0, (cudaStream_t)stream);
+}
+
+extern "C" int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
+                             int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream) {
+    SPB_CHECK_ARG(d_u_hi && d_u_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
+    return wino_gemm_tc((const __half *)d_u_hi, (const __half *)d_u_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
+                        d_out, rows_pad, cols, inv_scale, (cudaStream_t)stream);
 }
 
 #define SPB_TRY(expr)                 \
@@ -1011,7 +1013,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
     prof_begin(kTagPrep, s);
-    SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, 0, stream));
+    SPB_TRY(spb_split_fp16(io->d_vf, ws.vf_hi, ws.vf_lo, N, kE, kHW, 1, 1.0f, stream));
     vfmean_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(io->d_vf, ws.vfmean, N);
     SPB_LAUNCH_CHECK();
     prof_end(s);
@@ -1058,7 +1060,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         prof_end(s);
         const int cur = t & 1, nxt = cur ^ 1;
         if (wino) {
-            // 3x3 gate convolutions of h as Winograd F(2x2,3x3): input transform, 16 per-position GEMMs
+            // 3x3 gate convolutions of h as Winograd F(2x4,3x3): input transform, 24 per-position GEMMs
             // on tcgen05, output transform folded into the ConvLSTM cell.  h(0) = 0 -> nothing to multiply.
             if (t > 0) {
                 prof_begin(kTagCell, s);
@@ -1067,10 +1069,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                 SPB_LAUNCH_CHECK();
                 prof_end(s);
                 prof_begin(kTagConvH, s);
-                ConvGemmArgs a{ws.u_hi, ws.u_lo, (const __half *)w->ww_hi, (const __half *)w->ww_lo, w->d_wino_row_base,
-                               16 * (int64_t)kGateCols, nullptr, ws.wm, kGateCols, 16, kGateCols, 1, w->inv_scale_w / kWinoActScale};
-                a.rows_per_img = (int)ws.rows_pad;
-                SPB_TRY(conv_gemm_tc(a, s));
+                SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->ww_hi, (const __half *)w->ww_lo, ws.wm, ws.rows_pad,
+                                     kGateCols, w->inv_scale_w, s));
                 prof_end(s);
             }
             prof_begin(kTagCell, s);

@@ -15,7 +15,6 @@ constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
 //   w  = w_hi + w_lo / 2^11   fp16 [rows, ks*ks*512], K index = (ky*ks+kx)*512 + ci, pre-multiplied by 1/inv_scale
 //   row of w used for output column `col` of image n:  w_row_base[n] + col   (w_row_base NULL -> 0)
-// ks = 1 turns the kernel into a plain batched GEMM (n_images = batch, rows_per_img rows each).
 struct ConvGemmArgs {
     const __half *a_hi, *a_lo;
     const __half *w_hi, *w_lo;
@@ -26,7 +25,6 @@ struct ConvGemmArgs {
     int64_t ldo;
     int n_images, cols, ks;
     float inv_scale;
-    int rows_per_img = 0;             // ks = 1 only: rows per batch entry (multiple of 240)
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].
@@ -37,5 +35,9 @@ __host__ __device__ inline int gate_col(int ch, int g) {
 
 int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s);
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s);     // tcgen05 / TMEM / TMA (conv_tc.cu)
+// the 24 Winograd F(2x4,3x3) per-position GEMMs + the row half of the output transform (conv_tc.cu):
+// u [24][rows_pad][512], w [24*cols][512] fp16 pairs (position 4j+i) -> out [12][cols/128][rows_pad][128] fp32
+int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s);
 
 }  // namespace spb

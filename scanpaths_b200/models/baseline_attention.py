@@ -37,16 +37,14 @@ GATES_X = ("input_x", "forget_x", "output_x", "memory_x")
 DecoderWeights, DecoderIO = _lib.DecoderWeights, _lib.DecoderIO
 
 
-def split_pair(w: torch.Tensor, lo_unscaled=False):
-    """fp32 tensor -> (hi, lo) fp16 with w * scale = hi + lo / 2^11 (or hi + lo when lo_unscaled),
-    scale a power of two that puts max|w| in [32, 64) ([2^13, 2^14) when lo_unscaled, so that the
-    unscaled low half stays a normal fp16 for all but negligible weights).  Returns (hi, lo, 1/scale)."""
+def split_pair(w: torch.Tensor):
+    """fp32 tensor -> (hi, lo) fp16 with w * scale = hi + lo / 2^11, scale a power of two that puts
+    max|w| in [32, 64).  Returns (hi, lo, 1/scale)."""
     mx = float(w.abs().max())
-    top = 13 if lo_unscaled else 5
-    scale = 2.0 ** (top - math.floor(math.log2(mx))) if mx > 0 else 1.0
+    scale = 2.0 ** (5 - math.floor(math.log2(mx))) if mx > 0 else 1.0
     ws = w.double() * scale
     hi = ws.to(torch.float16)
-    lo = (ws - hi.double()).to(torch.float16) if lo_unscaled else ((ws - hi.double()) * 2048.0).to(torch.float16)
+    lo = ((ws - hi.double()) * 2048.0).to(torch.float16)
     return hi.contiguous(), lo.contiguous(), 1.0 / scale
 
 
@@ -77,14 +75,17 @@ def prepare_weights(sd, task: str, device):
     wx = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_X])
     wh = _interleave_gates([_conv_to_gemm(f("lstm.%s.weight" % g)) for g in GATES_H])
     wp = torch.cat([_conv_to_gemm(f(s + ".weight")) for s in sets], 0).contiguous()
-    # Winograd F(2x2,3x3) weights of the h-gates: W'[pos = 4i+j] = (G g G^T)[i][j], composed in float64,
-    # rows gate-interleaved like wh, position-major: [16 * 2048, 512]
-    Gm = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64, device=device)
-    wino = [torch.einsum("ia,ocab,jb->oijc", Gm, f("lstm.%s.weight" % g).double(), Gm).reshape(512, 16 * 512)
+    # Winograd F(2x4,3x3) weights of the h-gates: W'[pos = 4j+i] = (G2 g G4^T)[i][j] (i: row position of F(2,3),
+    # j: column position of F(4,3) on the points 0, +-1, +-2, inf), composed in float64, rows gate-interleaved
+    # like wh, position-major: [24 * 2048, 512]
+    G2 = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64, device=device)
+    G4 = torch.tensor([[1 / 4, 0, 0], [-1 / 6, -1 / 6, -1 / 6], [-1 / 6, 1 / 6, -1 / 6], [1 / 24, 1 / 12, 1 / 6],
+                       [1 / 24, -1 / 12, 1 / 6], [0, 0, 1]], dtype=torch.float64, device=device)
+    wino = [torch.einsum("ia,ocab,jb->ojic", G2, f("lstm.%s.weight" % g).double(), G4).reshape(512, 24 * 512)
             for g in GATES_H]
-    ww = _interleave_gates(wino).view(2048, 16, 512).permute(1, 0, 2).reshape(16 * 2048, 512)
-    t["ww_hi"], t["ww_lo"], isw = split_pair(ww, lo_unscaled=True)
-    t["d_wino_row_base"] = (torch.arange(16, device=device, dtype=torch.int32) * 2048).contiguous()
+    ww = _interleave_gates(wino).view(2048, 24, 512).permute(1, 0, 2).reshape(24 * 2048, 512)
+    t["ww_hi"], t["ww_lo"], isw = split_pair(ww)
+    t["d_wino_row_base"] = (torch.arange(24, device=device, dtype=torch.int32) * 2048).contiguous()
     t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
     t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
     t["wp_hi"], t["wp_lo"], isp = split_pair(wp)
