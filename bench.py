@@ -300,29 +300,29 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
-    names = {1: "conv3x3_x", 2: "winograd_gemm_h", 3: "conv5x5", 4: "wino_input+lstm_cell", 5: "head", 6: "feedback",
-             7: "rank1", 8: "prep"}
+    names = {1: "conv3x3_x", 2: "winograd_gemm_h", 3: "conv5x5", 4: "lstm_cell", 5: "head", 6: "feedback",
+             7: "rank1", 8: "prep", 9: "wino_input"}
     share = {names[k]: float(ms_buf[tag_buf == k].sum()) for k in names if (tag_buf == k).any()}
     tot_tagged = sum(share.values()) or 1.0
     conv_h = ms_buf[tag_buf == 2]
     wave_imgs = min(args.wave, N)
-    # dominant kernel: gemm_tc_flat_kernel = the 16 per-position GEMMs of the Winograd F(2x2,3x3) form of the
-    # 3x3 gate convolution, [wave*300 tiles x 512] x [512 x 2048] each
-    flop_gemm = 16 * 2.0 * wave_imgs * 300 * 2048 * 512
+    # dominant kernel: wino_gemm_tc_kernel = the 24 per-position GEMMs of the Winograd F(2x4,3x3) form of the
+    # 3x3 gate convolution, [wave*150 tiles x 512] x [512 x 2048] each
+    flop_gemm = 24 * 2.0 * wave_imgs * 150 * 2048 * 512
     flop_direct = 2.0 * wave_imgs * 1200 * 2048 * 4608
     roofline = None
     if len(conv_h):
         avg_ms = float(conv_h.mean())
         ach = flop_gemm / (avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": "gemm_tc_flat_kernel (Winograd F(2x2,3x3) gate convolution: 16 per-position GEMMs, "
+        roofline = {"kernel": "wino_gemm_tc_kernel (Winograd F(2x4,3x3) gate convolution: 24 per-position GEMMs, "
                               "%d images per launch)" % wave_imgs,
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "traffic": None, "peak_source": which, "avg_launch_ms": avg_ms, "launches": int(len(conv_h)),
                     "issued_tflops": 3 * ach, "issued_frac": 3 * ach / peak_tf,
                     "direct_conv_equivalent_tflops": flop_direct / (avg_ms * 1e-3) / 1e12,
-                    "note": "achieved counts the ALGORITHMIC flops of this kernel (2*M*N*K of its 16 GEMMs = %.2f "
-                            "TFLOP per launch); it issues 3 fp16 MMAs per algorithmic MMA (hi*hi, hi*lo, lo*hi) for "
-                            "fp32-equivalent results, so frac tops out at 1/3; the same convolution done directly "
+                    "note": "achieved counts the ALGORITHMIC flops of this kernel (2*M*N*K of its 24 GEMMs = %.2f "
+                            "TFLOP per launch); it issues 3 fp16 MMA flops per algorithmic flop (hi*hi, hi*lo, lo*hi) "
+                            "for fp32-equivalent results, so frac tops out at 1/3; the same convolution done directly "
                             "would need %.2f TFLOP" % (flop_gemm / 1e12, flop_direct / 1e12),
                     "time_share_of_tagged_kernels": {k: v / tot_tagged for k, v in share.items()}}
 

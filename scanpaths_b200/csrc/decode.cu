@@ -374,32 +374,44 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
 constexpr int kTilesY = 15, kTilesX = 10, kTilesPerImg = 150;
 constexpr int kWinoPos = 24;        // position p = 4j + i (i: F(2,3) row position, j: F(4,3) column position)
 
-// U[p][n*150 + tile][ci] = (B2^T d B4)[i][j]; one block per (image, tile), thread = 4 channels.
-__global__ void __launch_bounds__(128)
+// U[p][n*150 + tile][ci] = (B2^T d B4)[i][j]; one block per (image, tile), thread = 2 channels (the kernel is
+// latency-bound: 2 channels per thread keep it at ~70 registers, i.e. 3 x 8 warps per SM in flight).
+__global__ void __launch_bounds__(256, 3)
 wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, __half *__restrict__ u_hi,
                   __half *__restrict__ u_lo, int64_t rows_pad) {
     const int64_t nt = blockIdx.x;                   // n*150 + tile
     const int64_t n = nt / kTilesPerImg;
     const int tile = (int)(nt - n * kTilesPerImg);
     const int ty = tile / kTilesX, tx = tile - ty * kTilesX;
-    const int c0 = threadIdx.x * 4;
-    // column by column of the 4 x 6 patch: B2^T on the 4 rows first, so that only u[4][6] stays live
-    float u[4][6][4];
+    const int c0 = threadIdx.x * 2;
+    // all 48 loads of the 4 x 6 patch are issued before the first use (one memory round trip per block):
+    // out-of-image pixels load from a clamped address and are zeroed afterwards
+    uint32_t rh[4][6], rl[4][6];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int yy = min(max(2 * ty - 1 + a, 0), kH - 1), xx = min(max(4 * tx - 1 + b, 0), kW - 1);
+            const int64_t off = ((n * kH + yy) * kW + xx) * (int64_t)kE + c0;
+            rh[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_hi + off));
+            rl[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_lo + off));
+        }
+    float u[4][6][2];
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
-        float d[4][4];
+        float d[4][2];
         const int xx = 4 * tx - 1 + b;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int yy = 2 * ty - 1 + a;
-            if (yy >= 0 && yy < kH && xx >= 0 && xx < kW) {
-                load_h4(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + c0, d[a]);
-            } else {
-                d[a][0] = d[a][1] = d[a][2] = d[a][3] = 0.0f;
-            }
+            const bool in = yy >= 0 && yy < kH && xx >= 0 && xx < kW;
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&rh[a][b]));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&rl[a][b]));
+            d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
+            d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
             u[0][b][e] = d[0][e] - d[2][e];
             u[1][b][e] = d[1][e] + d[2][e];
             u[2][b][e] = d[2][e] - d[1][e];
@@ -408,9 +420,9 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float t[6][4];
+        float t[6][2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
             const float d0 = u[i][0][e], d1 = u[i][1][e], d2 = u[i][2][e], d3 = u[i][3][e], d4 = u[i][4][e], d5 = u[i][5][e];
             t[0][e] = fmaf(4.0f, d0, fmaf(-5.0f, d2, d4));
             t[1][e] = fmaf(-4.0f, d1 + d2, d3 + d4);
@@ -421,16 +433,12 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            __half hh[4], hl[4];
+            __half hh[2], hl[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_one(t[j][e], hh[e], hl[e]);
+            for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
             const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
-            *reinterpret_cast<uint2 *>(u_hi + off) =
-                make_uint2((uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16),
-                           (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16));
-            *reinterpret_cast<uint2 *>(u_lo + off) =
-                make_uint2((uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16),
-                           (uint32_t)__half_as_ushort(hl[2]) | ((uint32_t)__half_as_ushort(hl[3]) << 16));
+            *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+            *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
         }
     }
 }
@@ -438,9 +446,9 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
 // ConvLSTM cell with the column half of the Winograd output transform folded in: block = (tile row ty, image,
 // 128-channel group), thread = channel, loop over the 10 tiles of the row; per tile and gate the 12 planes
 // t[r][j] = (A2^T m)[r][j] of the GEMM (coalesced 128-byte lines) give the 2 x 4 pre-activations t . A4.
-// M == NULL means h = 0 (first step).  HBM: 12 x 2 KB (M) + 8 x 8 KB (xg) + c, h per tile and 128 channels.
-template <int S>
-__global__ void __launch_bounds__(128)
+// HAS_M = false means h = 0 (first step).  HBM: 12 x 2 KB (M) + 8 x 8 KB (xg) + c, h per tile and 128 channels.
+template <int S, bool HAS_M>
+__global__ void __launch_bounds__(128, S == 1 ? 4 : 3)
 lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ xg,
                       const float *__restrict__ V, const float *__restrict__ sp_mem, float *__restrict__ c,
                       __half *__restrict__ h_hi, __half *__restrict__ h_lo) {
@@ -464,53 +472,68 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
     __syncthreads();
     const int gc = gate_col(ch, 0);
     for (int tx = 0; tx < kTilesX; ++tx) {
-        float pre[4][8];                              // [gate][oy*4 + ox]
         const int64_t row = n * kTilesPerImg + ty * kTilesX + tx;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int r = 0; r < 2; ++r) {
+            // all loads of the half tile (24 GEMM planes, 16 x-gates, 4 cell states) are issued before the
+            // first use: one memory round trip per half tile instead of one per gate / pixel
+            float t[4][6], xv[4][4], cv[4];
+            const int64_t pix0 = n * kHW + (2 * ty + r) * kW + 4 * tx;
+            if (HAS_M) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                float t[6];
+                for (int g = 0; g < 4; ++g)
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    t[j] = M ? M[(((int64_t)(2 * j + r) * (kGateCols / 128) + (gc >> 7)) * rows_pad + row) * 128 + (gc & 127) + g * 32]
-                             : 0.0f;
-                const float s12 = t[1] + t[2], d12 = t[1] - t[2], s34 = t[3] + t[4], d34 = t[3] - t[4];
-                pre[g][4 * r + 0] = (t[0] + s12) + s34;
-                pre[g][4 * r + 1] = fmaf(2.0f, d34, d12);
-                pre[g][4 * r + 2] = fmaf(4.0f, s34, s12);
-                pre[g][4 * r + 3] = fmaf(8.0f, d34, d12) + t[5];
+                    for (int j = 0; j < 6; ++j)
+                        t[g][j] = __ldg(M + (((int64_t)(2 * j + r) * (kGateCols / 128) + (gc >> 7)) * rows_pad + row) * 128 +
+                                        (gc & 127) + g * 32);
             }
-        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int oy = q >> 2, ox = q & 3;
-            const int64_t pix = n * kHW + (2 * ty + oy) * kW + 4 * tx + ox;
-            const float *xp = xg + pix * kGateCols + gc;
-            float p0 = pre[0][q] + xp[0], p1 = pre[1][q] + xp[32], p2 = pre[2][q] + xp[64];
-            const float p3 = pre[3][q] + xp[96];
-            const float cold = c[pix * kE + ch];
+            for (int ox = 0; ox < 4; ++ox) {
 #pragma unroll
-            for (int st = 0; st < S; ++st) {
-                float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+                for (int g = 0; g < 4; ++g) xv[ox][g] = __ldg(xg + (pix0 + ox) * kGateCols + gc + g * 32);
+                cv[ox] = c[(pix0 + ox) * kE + ch];
+            }
+            float pre[4][4];                          // [gate][ox] of output row r
 #pragma unroll
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    const float sv = halo[st][oy + t9 / 3][4 * tx + ox + t9 % 3];
-                    r0 = fmaf(v[st][0][t9], sv, r0);
-                    r1 = fmaf(v[st][1][t9], sv, r1);
-                    r2 = fmaf(v[st][2][t9], sv, r2);
+            for (int g = 0; g < 4; ++g) {
+                if (HAS_M) {
+                    const float s12 = t[g][1] + t[g][2], d12 = t[g][1] - t[g][2], s34 = t[g][3] + t[g][4], d34 = t[g][3] - t[g][4];
+                    pre[g][0] = (t[g][0] + s12) + s34;
+                    pre[g][1] = fmaf(2.0f, d34, d12);
+                    pre[g][2] = fmaf(4.0f, s34, s12);
+                    pre[g][3] = fmaf(8.0f, d34, d12) + t[g][5];
+                } else {
+                    pre[g][0] = pre[g][1] = pre[g][2] = pre[g][3] = 0.0f;
                 }
-                p0 += r0; p1 += r1; p2 += r2;
             }
-            const float gi = __frcp_rn(1.0f + __expf(-p0));
-            const float gf = __frcp_rn(1.0f + __expf(-p1));
-            const float go = __frcp_rn(1.0f + __expf(-p2));
-            const float gg = 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * p3));
-            const float cn = gf * cold + gi * gg;
-            c[pix * kE + ch] = cn;
-            __half hh, hl;
-            split_one(go * cn, hh, hl);
-            h_hi[pix * kE + ch] = hh; h_lo[pix * kE + ch] = hl;
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox) {
+                const int64_t pix = pix0 + ox;
+                float p0 = pre[0][ox] + xv[ox][0], p1 = pre[1][ox] + xv[ox][1], p2 = pre[2][ox] + xv[ox][2];
+                const float p3 = pre[3][ox] + xv[ox][3];
+                const float cold = cv[ox];
+#pragma unroll
+                for (int st = 0; st < S; ++st) {
+                    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const float sv = halo[st][r + t9 / 3][4 * tx + ox + t9 % 3];
+                        r0 = fmaf(v[st][0][t9], sv, r0);
+                        r1 = fmaf(v[st][1][t9], sv, r1);
+                        r2 = fmaf(v[st][2][t9], sv, r2);
+                    }
+                    p0 += r0; p1 += r1; p2 += r2;
+                }
+                const float gi = __frcp_rn(1.0f + __expf(-p0));
+                const float gf = __frcp_rn(1.0f + __expf(-p1));
+                const float go = __frcp_rn(1.0f + __expf(-p2));
+                const float gg = 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * p3));
+                const float cn = gf * cold + gi * gg;
+                c[pix * kE + ch] = cn;
+                __half hh, hl;
+                split_one(go * cn, hh, hl);
+                h_hi[pix * kE + ch] = hh; h_lo[pix * kE + ch] = hl;
+            }
         }
     }
 }
@@ -1063,8 +1086,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             // 3x3 gate convolutions of h as Winograd F(2x4,3x3): input transform, 24 per-position GEMMs
             // on tcgen05, output transform folded into the ConvLSTM cell.  h(0) = 0 -> nothing to multiply.
             if (t > 0) {
-                prof_begin(kTagCell, s);
-                wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 128, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
+                prof_begin(kTagWinoIn, s);
+                wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 256, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
                                                                              ws.rows_pad);
                 SPB_LAUNCH_CHECK();
                 prof_end(s);
@@ -1074,13 +1097,11 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                 prof_end(s);
             }
             prof_begin(kTagCell, s);
-            const float *Mp = t > 0 ? ws.wm : nullptr;
-            if (S == 1)
-                lstm_cell_wino_kernel<1><<<dim3(kTilesY, (unsigned)N, kE / 128), 128, 0, s>>>(
-                    Mp, ws.rows_pad, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
-            else
-                lstm_cell_wino_kernel<2><<<dim3(kTilesY, (unsigned)N, kE / 128), 128, 0, s>>>(
-                    Mp, ws.rows_pad, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt]);
+            const dim3 cg(kTilesY, (unsigned)N, kE / 128);
+#define SPB_CELL_WINO(S_, M_) lstm_cell_wino_kernel<S_, M_><<<cg, 128, 0, s>>>(ws.wm, ws.rows_pad, ws.xg, ws.V, ws.sp_mem, ws.c, ws.h_hi[nxt], ws.h_lo[nxt])
+            if (S == 1) { if (t > 0) SPB_CELL_WINO(1, true); else SPB_CELL_WINO(1, false); }
+            else { if (t > 0) SPB_CELL_WINO(2, true); else SPB_CELL_WINO(2, false); }
+#undef SPB_CELL_WINO
             SPB_LAUNCH_CHECK();
             prof_end(s);
         } else {
