@@ -193,9 +193,9 @@ typedef struct spb_decoder_weights {
     const void *wx_hi, *wx_lo;       /* fp16 [2048, 4608]  lstm.*_x                     */
     const void *wh_hi, *wh_lo;       /* fp16 [2048, 4608]  lstm.*_h                     */
     const void *wp_hi, *wp_lo;       /* fp16 [n_weight_sets*512, 12800]  5x5 layer(s)   */
-    const void *ww_hi, *ww_lo;       /* fp16 [16*2048, 512] Winograd-transformed lstm.*_h: G g G^T, position-major, */
-                                     /*   UNSCALED low half: w * scale = hi + lo           */
-    const int32_t *d_wino_row_base;  /* [16] = position * 2048                          */
+    const void *ww_hi, *ww_lo;       /* fp16 [24*2048, 512] Winograd F(2x4,3x3)-transformed lstm.*_h: G2 g G4^T,     */
+                                     /*   position-major, position = 4*(column position j) + (row position i)   */
+    const int32_t *d_wino_row_base;  /* [24] = position * 2048                          */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
     const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */
@@ -209,7 +209,8 @@ typedef struct spb_decoder_weights {
     const float *b_semantic_embed;   /* [512] */
     /* composed head (tensor-core path): the 5x5 layer feeds sal_layer_2, sal_layer_3 and drt_layer_1
      * with no nonlinearity in between, so they collapse into effective kernels on h:          */
-    const float *w23_eff;            /* [n_weight_sets, 25, 512, 2] 5x5 -> (stop map, action map) */
+    const void *w23_hi, *w23_lo;     /* fp16 [n_weight_sets*128, 512] 5x5 -> (stop map, action map) as a per-pixel */
+                                     /*   GEMM: row = tap*2 + map (rows 50..127 zero)                          */
     const float *b23_eff;            /* [n_weight_sets, 2]  incl. sal_layer_2/3 bias             */
     const float *wd_eff;             /* [n_weight_sets, 4, 121, 512] 11x11 stride-5 duration conv; variant = */
                                      /*   2*(window in top row) + (window in left column): taps of drt_layer_1 */
@@ -218,7 +219,7 @@ typedef struct spb_decoder_weights {
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;
-    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_23;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
     int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
     int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
     int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
@@ -227,7 +228,7 @@ typedef struct spb_decoder_weights {
 
 typedef struct spb_decoder_io {
     int32_t n_images, steps;
-    int32_t use_tensor_cores;        /* 1: tcgen05, Winograd F(2x2,3x3) gate GEMMs + composed head (product path); */
+    int32_t use_tensor_cores;        /* 1: tcgen05, Winograd F(2x4,3x3) gate GEMMs + composed head (product path); */
                                      /* 2: tcgen05 direct 3x3 implicit GEMM + composed head; 0: SIMT fp32 check kernels */
     int32_t reserved;
     const float *d_vf;               /* [N, 512, 30, 40] visual_feature (NCHW, as the encoder emits it) */
@@ -244,7 +245,7 @@ int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t
 int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream);
 
 /* One implicit-GEMM convolution on its own (unit tests / profiling of the kernel):
- * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]  (ks = 3, 5; operand pairs
+ * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]  (ks = 1, 3, 5; operand pairs
  * x = hi + lo/2^11, a NHWC [N,30,40,512], w [rows, ks*ks*512]). */
 int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, const void *d_w_lo,
                   const int32_t *d_w_row_base, int64_t w_rows, const float *d_bias, float *d_out, int64_t ldo,

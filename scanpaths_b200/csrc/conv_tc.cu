@@ -190,7 +190,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int c_tile = tile % nct, p_tile = (tile / nct) % kPT, img = tile / (nct * kPT);
-                const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
+                const int row_base = (a.w_row_base ? a.w_row_base[img] / a.w_row_div : 0) + c_tile * kTileCh;
                 const int y0 = p_tile * (kTilePix / kW);
                 for (int kb = 0; kb < kNumKB; ++kb, ++it) {
                     const int s = it % kStages;
@@ -360,7 +360,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             // memory and one thread hands the box to the TMA store engine; the 4-byte-per-lane global
             // stores this replaces kept the drain warps busy for ~6k cycles per tile, longer than a
             // K = 512 tile of the Winograd path can hide.
-            const int row_base = (a.w_row_base ? a.w_row_base[img] : 0) + c_tile * kTileCh;
+            const int row_base = (a.w_row_base ? a.w_row_base[img] / a.w_row_div : 0) + c_tile * kTileCh;
             const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
             const uint32_t stage_out = out_smem + half * kOutBytes;
             const int64_t row0 = (int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix;
@@ -648,9 +648,10 @@ static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, i
 
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
-    // ks = 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11
-    if (a.cols % kTileCh != 0 || (a.ks != 3 && a.ks != 5) || a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0) {
-        set_error("conv_gemm_tc: cols must be a multiple of %d, ks 3 or 5, out 16-byte aligned", kTileCh);
+    // ks = 1 / 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11
+    if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0 ||
+        a.w_row_div < 1) {
+        set_error("conv_gemm_tc: cols must be a multiple of %d, ks 1, 3 or 5, out 16-byte aligned", kTileCh);
         return SPB_ERR_ARG;
     }
     if (get_encode() == nullptr) {
@@ -679,7 +680,8 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
 #define SPB_LAUNCH_TC(KS_)                                                                                          \
     SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
     conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, kHW)
-    if (a.ks == 3) { SPB_LAUNCH_TC(3); }
+    if (a.ks == 1) { SPB_LAUNCH_TC(1); }
+    else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
     else { SPB_LAUNCH_TC(5); }
 #undef SPB_LAUNCH_TC
     SPB_LAUNCH_CHECK();

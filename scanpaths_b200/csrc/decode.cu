@@ -135,7 +135,7 @@ conv_gemm_simt_kernel(ConvGemmArgs a) {
         if (nvalid) {
             // all rows of one block belong to the image of its first pixel row only when w_row_base is
             // NULL; otherwise resolve per output row below (done in the epilogue loop through `img`)
-            const int64_t base = a.w_row_base ? a.w_row_base[m0 / kHW] : 0;
+            const int64_t base = a.w_row_base ? a.w_row_base[m0 / kHW] / a.w_row_div : 0;
             const int64_t off = (base + wcol) * (int64_t)K + k0 + lk;
             for (int e = 0; e < 4; ++e)
                 bv[e] = __half2float(a.w_hi[off + e]) + __half2float(a.w_lo[off + e]) * (1.0f / kLoScale);
@@ -158,7 +158,7 @@ conv_gemm_simt_kernel(ConvGemmArgs a) {
         for (int j = 0; j < 4; ++j) {
             const int col = n0 + tx * 4 + j;
             if (col >= a.cols) continue;
-            const int64_t base = a.w_row_base ? a.w_row_base[m / kHW] : 0;
+            const int64_t base = a.w_row_base ? a.w_row_base[m / kHW] / a.w_row_div : 0;
             float v = acc[i][j] * a.inv_scale;
             if (a.bias) v += a.bias[base + col];
             a.out[m * a.ldo + col] = v;
@@ -597,107 +597,41 @@ head_reduce_kernel(const float *__restrict__ feat, int HD, const float *__restri
 //   * an 11x11 stride-5 convolution 512 -> 1 on 48 windows (4 border variants): 6 MFLOP,
 // with effective kernels composed once in float64 (prepare_weights).  h is read as the same fp16
 // (hi, lo) pair the gate GEMM consumes.
+// The 5x5 -> 2 convolution runs as a per-pixel GEMM on the tensor cores: Z[p][tap*2 + map] = h[p,:] . w23[tap,map,:]
+// (conv_gemm_tc with ks = 1: 128 weight rows per head, 50 used; h is read once) followed by the 25-tap
+// gather below, y[p] = sum_tap Z[p + tap][tap] -- the direct SIMT form of this convolution was FMA-bound
+// at 0.77 ms per 256-image step.
 // ---------------------------------------------------------------------------
+constexpr int kHeadCols = 128;       // GEMM columns (weight rows) per head: 25 taps x 2 maps, zero-padded
 
-
-// y2[p], y3[p] for a 3-row pixel tile of one (image, head): a register-tiled direct convolution.
-// Per 64-channel chunk the 7 x 44 halo of h (fp32, rebuilt from the hi/lo pair, zero outside the
-// image) and the chunk's weights [25][64][2] are staged in shared memory; lane l owns channels
-// (2l, 2l+1) of the chunk, a warp owns 8-pixel row segments, and per filter row a lane loads 12
-// h pairs + 5 weight quads for 160 FMAs.  Channel partial sums stay in registers across all 8
-// chunks and are reduced across the warp once.  ~1.6 GB of L2 traffic per 256-image step instead
-// of 15.7 GB for the naive gather; FMA-bound.
-constexpr int kMapsChunk = 64, kHaloH = 7, kHaloW = 44;
-constexpr int kMapsSmemBytes = (kHaloH * kHaloW * kMapsChunk + 25 * kMapsChunk * 2) * 4;   // 91,648 B
-__global__ void __launch_bounds__(256, 2)
-head_maps_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ w23,
-                 const float *__restrict__ b23, const int32_t *__restrict__ w_row_base, int HD,
-                 float *__restrict__ y2, float *__restrict__ y3) {
-    extern __shared__ float sm[];
-    float *hs = sm;                                          // [7][44][64]
-    float *ws = sm + kHaloH * kHaloW * kMapsChunk;           // [25][64][2]
-    const int64_t nh = blockIdx.y;
+// one thread per (image, head, pixel): 25 float2 loads from Z (L2-resident), zero padding by bounds
+__global__ void __launch_bounds__(256)
+head_gather_kernel(const float *__restrict__ z, int ldz, const float *__restrict__ b23,
+                   const int32_t *__restrict__ w_row_base, int HD, float *__restrict__ y2, float *__restrict__ y3,
+                   int64_t total) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t nh = idx / kHW;
+    const int p = (int)(idx - nh * kHW);
     const int64_t n = nh / HD;
     const int hd = (int)(nh % HD);
     const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
-    const int y0 = blockIdx.x * 3;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *wset = w23 + (int64_t)set * 25 * kE * 2;
-    float acc[2][8][2];
+    const int y = p / kW, x = p - y * kW;
+    const float *zb = z + n * kHW * (int64_t)ldz + hd * kHeadCols;
+    float2 v[25];
 #pragma unroll
-    for (int sg = 0; sg < 2; ++sg)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[sg][i][0] = 0.0f; acc[sg][i][1] = 0.0f; }
-
-    for (int chunk = 0; chunk < kE / kMapsChunk; ++chunk) {
-        __syncthreads();                                     // previous chunk fully consumed
-        // ---- stage the halo: item = (halo pixel, 8-channel group)
-        for (int it = threadIdx.x; it < kHaloH * kHaloW * (kMapsChunk / 8); it += 256) {
-            const int grp = it & 7, hp = it >> 3;
-            const int hy = hp / kHaloW, hx = hp - hy * kHaloW;
-            const int yy = y0 - 2 + hy, xx = hx - 2;
-            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (yy >= 0 && yy < kH && xx >= 0 && xx < kW)
-                load_h8(h_hi, h_lo, ((n * kH + yy) * kW + xx) * (int64_t)kE + chunk * kMapsChunk + grp * 8, v);
-            float4 *dst = reinterpret_cast<float4 *>(hs + hp * kMapsChunk + grp * 8);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        for (int it = threadIdx.x; it < 25 * kMapsChunk * 2 / 4; it += 256) {
-            const int tap = it / (kMapsChunk * 2 / 4), r4 = it - tap * (kMapsChunk * 2 / 4);
-            reinterpret_cast<float4 *>(ws)[it] =
-                *reinterpret_cast<const float4 *>(wset + ((int64_t)tap * kE + chunk * kMapsChunk) * 2 + r4 * 4);
-        }
-        __syncthreads();
-        // ---- compute: warp w owns segments w and w + 8 (15 segments of 8 pixels)
-#pragma unroll
-        for (int sg = 0; sg < 2; ++sg) {
-            const int seg = warp + 8 * sg;
-            if (seg < 15) {
-                const int row = seg / 5, x0 = (seg % 5) * 8;
-#pragma unroll 1
-                for (int ky = 0; ky < 5; ++ky) {
-                    float2 hr[12];
-                    const float *hp = hs + ((row + ky) * kHaloW + x0) * kMapsChunk + 2 * lane;
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) hr[i] = *reinterpret_cast<const float2 *>(hp + i * kMapsChunk);
-#pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) {
-                        const float4 w4 = *reinterpret_cast<const float4 *>(ws + ((ky * 5 + kx) * kMapsChunk + 2 * lane) * 2);
-#pragma unroll
-                        for (int px = 0; px < 8; ++px) {
-                            const float2 hv = hr[px + kx];
-                            acc[sg][px][0] = fmaf(hv.x, w4.x, acc[sg][px][0]);
-                            acc[sg][px][1] = fmaf(hv.x, w4.y, acc[sg][px][1]);
-                            acc[sg][px][0] = fmaf(hv.y, w4.z, acc[sg][px][0]);
-                            acc[sg][px][1] = fmaf(hv.y, w4.w, acc[sg][px][1]);
-                        }
-                    }
-                }
-            }
-        }
+    for (int tap = 0; tap < 25; ++tap) {
+        const int yy = min(max(y + tap / 5 - 2, 0), kH - 1), xx = min(max(x + tap % 5 - 2, 0), kW - 1);
+        v[tap] = __ldg(reinterpret_cast<const float2 *>(zb + (int64_t)(yy * kW + xx) * ldz + tap * 2));
     }
-    const float bias2 = b23[set * 2], bias3 = b23[set * 2 + 1];
+    float s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-    for (int sg = 0; sg < 2; ++sg) {
-        const int seg = warp + 8 * sg;
-        if (seg < 15) {                                      // warp-uniform
-            const int row = seg / 5, x0 = (seg % 5) * 8;
-#pragma unroll
-            for (int px = 0; px < 8; ++px) {
-                float s2 = acc[sg][px][0], s3 = acc[sg][px][1];
-                for (int o = 16; o > 0; o >>= 1) {
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-                }
-                if (lane == 0) {
-                    const int64_t o = nh * kHW + (y0 + row) * kW + x0 + px;
-                    y2[o] = s2 + bias2;      // b2 / b3 are folded into b23_eff
-                    y3[o] = s3 + bias3;
-                }
-            }
-        }
+    for (int tap = 0; tap < 25; ++tap) {
+        const int yy = y + tap / 5 - 2, xx = x + tap % 5 - 2;
+        if (yy >= 0 && yy < kH && xx >= 0 && xx < kW) { s2 += v[tap].x; s3 += v[tap].y; }
     }
+    y2[idx] = s2 + b23[set * 2];         // b2 / b3 are folded into b23_eff
+    y3[idx] = s3 + b23[set * 2 + 1];
 }
 
 // duration pre-activation of the 48 windows: one 4-warp block per (image, head, window); the 121
@@ -913,6 +847,7 @@ struct Workspace {
     int64_t rows_pad;
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
+    float *z23;            // composed-head GEMM result [N*1200][HD*128] (aliases feat: the two routes never meet)
     int64_t bytes;
 };
 
@@ -936,6 +871,7 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.c = (float *)take(N * kHW * kE * 4);
     w.acc = (float *)take(N * kHW * kGateCols * 4);
     w.feat = (float *)take(N * kHW * HD * kE * 4);
+    w.z23 = w.feat;
     w.V = (float *)take(N * S * 3 * kE * 9 * 4);
     w.y2 = (float *)take(N * HD * kHW * 4);
     w.y3 = (float *)take(N * HD * kHW * 4);
@@ -996,7 +932,7 @@ extern "C" int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void 
                              int64_t ldo, int32_t n_images, int32_t cols, int32_t ks, float inv_scale,
                              int32_t use_tensor_cores, spb_stream stream) {
     SPB_CHECK_ARG(d_a_hi && d_a_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
-    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
+    SPB_CHECK_ARG(n_images > 0 && cols > 0 && (ks == 1 || ks == 3 || ks == 5) && ldo >= cols, "bad sizes");
     ConvGemmArgs a{(const __half *)d_a_hi, (const __half *)d_a_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
                    d_w_row_base, w_rows, d_bias, d_out, ldo, n_images, cols, ks, inv_scale};
     return conv_gemm(a, use_tensor_cores != 0, (cudaStream_t)stream);
@@ -1134,9 +1070,15 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         if (tc) {
             // composed head straight from h: stop / action maps + duration windows (no 5x5 GEMM)
             prof_begin(kTagHead, s);
-            SPB_CUDA(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMapsSmemBytes));
-            head_maps_kernel<<<dim3(kHW / 120, (unsigned)(N * HD)), 256, kMapsSmemBytes, s>>>(
-                ws.h_hi[nxt], ws.h_lo[nxt], w->w23_eff, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3);
+            {
+                ConvGemmArgs a{ws.h_hi[nxt], ws.h_lo[nxt], (const __half *)w->w23_hi, (const __half *)w->w23_lo,
+                               io->d_w_row_base, (int64_t)w->n_weight_sets * kHeadCols, nullptr, ws.z23,
+                               (int64_t)HD * kHeadCols, (int)N, HD * kHeadCols, 1, w->inv_scale_23};
+                a.w_row_div = kE / kHeadCols;        // d_w_row_base counts rows of the 5x5 layer (512 per set)
+                SPB_TRY(conv_gemm_tc(a, s));
+            }
+            head_gather_kernel<<<(unsigned)((N * HD * kHW + 255) / 256), 256, 0, s>>>(
+                ws.z23, HD * kHeadCols, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3, N * HD * kHW);
             SPB_LAUNCH_CHECK();
             head_drt_kernel<<<(unsigned)(N * HD * 48), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
                                                                    io->d_w_row_base, HD, ws.drt_pre);

@@ -14,7 +14,7 @@ constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
 // One implicit-GEMM convolution:  out[(n*1200+p)*ldo + col] = inv_scale * conv(a, w)[p, col] (+ bias[col])
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
 //   w  = w_hi + w_lo / 2^11   fp16 [rows, ks*ks*512], K index = (ky*ks+kx)*512 + ci, pre-multiplied by 1/inv_scale
-//   row of w used for output column `col` of image n:  w_row_base[n] + col   (w_row_base NULL -> 0)
+//   row of w used for output column `col` of image n:  w_row_base[n] / w_row_div + col   (w_row_base NULL -> 0)
 struct ConvGemmArgs {
     const __half *a_hi, *a_lo;
     const __half *w_hi, *w_lo;
@@ -25,6 +25,7 @@ struct ConvGemmArgs {
     int64_t ldo;
     int n_images, cols, ks;
     float inv_scale;
+    int w_row_div = 1;            // w_row_base is given in units of w_row_div rows
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].

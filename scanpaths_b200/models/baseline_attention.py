@@ -121,7 +121,10 @@ def prepare_weights(sd, task: str, device):
     w3_64 = f("object_head.sal_layer_3.weight").double().reshape(512)
     wd_64 = f("object_head.drt_layer_1.weight").double()[0]                      # [c, 7, 7]
     w23 = torch.stack([torch.einsum("c,scikl->skli", w2_64, wp64), torch.einsum("c,scikl->skli", w3_64, wp64)], -1)
-    t["w23_eff"] = w23.reshape(len(sets), 25, 512, 2).float().contiguous()
+    # as rows of a per-pixel GEMM: [set][tap*2 + map][ci], zero-padded to 128 rows per set
+    w23g = torch.zeros((len(sets), 128, 512), dtype=torch.float64, device=device)
+    w23g[:, :50] = w23.reshape(len(sets), 25, 512, 2).permute(0, 1, 3, 2).reshape(len(sets), 50, 512)
+    t["w23_hi"], t["w23_lo"], is23 = split_pair(w23g.reshape(len(sets) * 128, 512))
     b23 = torch.stack([bp64 @ w2_64 + f("object_head.sal_layer_2.bias").double()[0],
                        bp64 @ w3_64 + f("object_head.sal_layer_3.bias").double()[0]], -1)
     t["b23_eff"] = b23.float().contiguous()
@@ -155,7 +158,7 @@ def prepare_weights(sd, task: str, device):
         "object_head.drt_layer_1.bias")
     bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
     w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
-    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w = isx, ish, isp, isw
+    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w, w.inv_scale_23 = isx, ish, isp, isw, is23
     w.n_streams = w.n_heads = len(streams)
     w.n_weight_sets = len(sets)
     return t, w

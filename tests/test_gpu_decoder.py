@@ -92,7 +92,7 @@ def test_conv_gemm_simt_vs_torch_fp64(lib, ks, cols):
     assert err < 1e-5 * mag, (err, mag)      # plain sequential fp32 accumulation over K = ks*ks*512
 
 
-@pytest.mark.parametrize("ks,cols,sets", [(3, 128, 0), (3, 2048, 0), (5, 512, 0), (5, 512, 3)])
+@pytest.mark.parametrize("ks,cols,sets", [(1, 256, 0), (1, 128, 3), (3, 128, 0), (3, 2048, 0), (5, 512, 0), (5, 512, 3)])
 def test_conv_gemm_tensor_core_vs_torch_fp64(lib, ks, cols, sets):
     err, mag = _conv_case(lib, ks, 3, cols, use_tc=True, per_image_sets=sets)
     print("tcgen05 conv ks=%d cols=%d max abs err %.3e (max |out| %.2f)" % (ks, cols, err, mag))
