@@ -195,6 +195,7 @@ typedef struct spb_decoder_weights {
     const void *wp_hi, *wp_lo;       /* fp16 [n_weight_sets*512, 12800]  5x5 layer(s)   */
     const void *ww_hi, *ww_lo;       /* fp16 [24*2048, 512] Winograd F(2x4,3x3)-transformed lstm.*_h: G2 g G4^T,     */
                                      /*   position-major, position = 4*(column position j) + (row position i)   */
+    const void *wwx_hi, *wwx_lo;     /* the same for lstm.*_x (the loop-invariant x-gate convolution)              */
     const int32_t *d_wino_row_base;  /* [24] = position * 2048                          */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
@@ -219,11 +220,10 @@ typedef struct spb_decoder_weights {
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;
-    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_23;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_wx, inv_scale_23;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
     int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
     int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
     int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
-    int32_t reserved;
 } spb_decoder_weights;
 
 typedef struct spb_decoder_io {

@@ -538,6 +538,33 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
     }
 }
 
+// Column half of the Winograd output transform on its own, for the loop-invariant x-gate convolution:
+// xg[pix][col] = (t . A4)[r][ox] + bias[col].  Block = (tile row, image, 128-column tile), thread = gate column.
+__global__ void __launch_bounds__(128)
+wino_output_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ bias, float *__restrict__ xg) {
+    const int64_t n = blockIdx.y;
+    const int ty = blockIdx.x, ct = blockIdx.z;
+    const float b = bias[ct * 128 + threadIdx.x];
+    for (int tx = 0; tx < kTilesX; ++tx) {
+        const int64_t row = n * kTilesPerImg + ty * kTilesX + tx;
+        float t[2][6];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                t[r][j] = __ldg(M + (((int64_t)(2 * j + r) * (kGateCols / 128) + ct) * rows_pad + row) * 128 + threadIdx.x);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float s12 = t[r][1] + t[r][2], d12 = t[r][1] - t[r][2], s34 = t[r][3] + t[r][4], d34 = t[r][3] - t[r][4];
+            float *o = xg + (n * kHW + (2 * ty + r) * kW + 4 * tx) * (int64_t)kGateCols + ct * 128 + threadIdx.x;
+            o[0] = ((t[r][0] + s12) + s34) + b;
+            o[kGateCols] = fmaf(2.0f, d34, d12) + b;
+            o[2 * kGateCols] = fmaf(4.0f, s34, s12) + b;
+            o[3 * kGateCols] = (fmaf(8.0f, d34, d12) + t[r][5]) + b;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Head, part 1 (predict_head.forward :141-150): per pixel, the channel dot products of
 // feat with sal_layer_2, sal_layer_3 and with the <= 4 drt_layer_1 taps under which the
@@ -977,7 +1004,15 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     SPB_LAUNCH_CHECK();
     prof_end(s);
     prof_begin(kTagConvX, s);
-    {
+    if (wino) {
+        // the loop-invariant x-gate convolution through the same Winograd F(2x4,3x3) kernels as the h-gates
+        wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
+        SPB_LAUNCH_CHECK();
+        SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->wwx_hi, (const __half *)w->wwx_lo, ws.wm, ws.rows_pad,
+                             kGateCols, w->inv_scale_wx, s));
+        wino_output_kernel<<<dim3(kTilesY, (unsigned)N, kGateCols / 128), 128, 0, s>>>(ws.wm, ws.rows_pad, w->bias_gate, ws.xg);
+        SPB_LAUNCH_CHECK();
+    } else {
         ConvGemmArgs a{ws.vf_hi, ws.vf_lo, (const __half *)w->wx_hi, (const __half *)w->wx_lo, nullptr, kGateCols,
                        w->bias_gate, ws.xg, kGateCols, (int)N, kGateCols, 3, w->inv_scale_x};
         SPB_TRY(conv_gemm(a, tc, s));

@@ -81,10 +81,12 @@ def prepare_weights(sd, task: str, device):
     G2 = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64, device=device)
     G4 = torch.tensor([[1 / 4, 0, 0], [-1 / 6, -1 / 6, -1 / 6], [-1 / 6, 1 / 6, -1 / 6], [1 / 24, 1 / 12, 1 / 6],
                        [1 / 24, -1 / 12, 1 / 6], [0, 0, 1]], dtype=torch.float64, device=device)
-    wino = [torch.einsum("ia,ocab,jb->ojic", G2, f("lstm.%s.weight" % g).double(), G4).reshape(512, 24 * 512)
-            for g in GATES_H]
-    ww = _interleave_gates(wino).view(2048, 24, 512).permute(1, 0, 2).reshape(24 * 2048, 512)
-    t["ww_hi"], t["ww_lo"], isw = split_pair(ww)
+    def wino_rows(gates):
+        mats = [torch.einsum("ia,ocab,jb->ojic", G2, f("lstm.%s.weight" % g).double(), G4).reshape(512, 24 * 512)
+                for g in gates]
+        return _interleave_gates(mats).view(2048, 24, 512).permute(1, 0, 2).reshape(24 * 2048, 512)
+    t["ww_hi"], t["ww_lo"], isw = split_pair(wino_rows(GATES_H))
+    t["wwx_hi"], t["wwx_lo"], iswx = split_pair(wino_rows(GATES_X))
     t["d_wino_row_base"] = (torch.arange(24, device=device, dtype=torch.int32) * 2048).contiguous()
     t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
     t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
@@ -158,7 +160,7 @@ def prepare_weights(sd, task: str, device):
         "object_head.drt_layer_1.bias")
     bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
     w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
-    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w, w.inv_scale_23 = isx, ish, isp, isw, is23
+    w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w, w.inv_scale_wx, w.inv_scale_23 = isx, ish, isp, isw, iswx, is23
     w.n_streams = w.n_heads = len(streams)
     w.n_weight_sets = len(sets)
     return t, w
