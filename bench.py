@@ -317,7 +317,11 @@ def main():
         roofline = {"kernel": "wino_gemm_tc_kernel (Winograd F(2x4,3x3) gate convolution: 24 per-position GEMMs, "
                               "%d images per launch)" % wave_imgs,
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": None, "peak_source": which, "avg_launch_ms": avg_ms, "launches": int(len(conv_h)),
+                    # DRAM bytes per launch from the committed ncu --set full capture (256 images:
+                    # dram__bytes_read 2.02 GB + dram__bytes_write 3.74 GB, profiles/r01_step_kernels_ncu_summary.csv);
+                    # algorithmic: 1.89 GB of U operands + 0.10 GB of weights + 3.77 GB of results
+                    "traffic": 5.762e9 * wave_imgs / 256.0, "traffic_unit": "B per launch (ncu, round 1)",
+                    "peak_source": which, "avg_launch_ms": avg_ms, "launches": int(len(conv_h)),
                     "issued_tflops": 3 * ach, "issued_frac": 3 * ach / peak_tf,
                     "direct_conv_equivalent_tflops": flop_direct / (avg_ms * 1e-3) / 1e12,
                     "note": "achieved counts the ALGORITHMIC flops of this kernel (2*M*N*K of its 24 GEMMs = %.2f "

@@ -2,9 +2,11 @@
 //
 // out[(img*1200 + p)*ldo + col] = inv_scale * sum_{tap,ci} a[img, p+tap, ci] * w[row(col), tap, ci] (+ bias)
 //
-// This is the dominant kernel of the decode path: the 3x3 gate convolutions of the ConvLSTM
-// (ConvLSTM.forward, OSIE/models/baseline_attention.py:39-42; per image 1200 pixels x 2048
-// outputs (4 gates x 512) x K = 9 x 512), once per step for h and once per image for x.
+// The convolutions of the decode path: the 3x3 gate convolutions of the ConvLSTM (ConvLSTM.forward,
+// OSIE/models/baseline_attention.py:39-42; per image 1200 pixels x 2048 outputs (4 gates x 512) x
+// K = 9 x 512, once per step for h and once per image for x) -- on the product path in their Winograd
+// F(2x4,3x3) form (wino_gemm_tc_kernel, second half of this file), as a direct implicit GEMM with
+// use_tensor_cores = 2 -- and the 1x1 / 5x5 convolutions of the head (ks = 1: the composed 5x5 -> 2 maps).
 //
 // Design
 //   * D^T = W . A^T: the UMMA "M" side is a tile of 128 OUTPUT CHANNELS (weights), the "N" side a
@@ -359,7 +361,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             // epilogue: each pixel half (4 warps = 128 channels) stages 30 pixels x 128 channels in shared
             // memory and one thread hands the box to the TMA store engine; the 4-byte-per-lane global
             // stores this replaces kept the drain warps busy for ~6k cycles per tile, longer than a
-            // K = 512 tile of the Winograd path can hide.
+            // K = 512 (ks = 1) tile can hide.
             const int row_base = (a.w_row_base ? a.w_row_base[img] / a.w_row_div : 0) + c_tile * kTileCh;
             const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
             const uint32_t stage_out = out_smem + half * kOutBytes;
