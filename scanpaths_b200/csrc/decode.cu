@@ -443,6 +443,13 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
     }
 }
 
+// 1 / x to 1 ulp in one MUFU (no slow-path branch like __frcp_rn; the gates go through __expf anyway)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ConvLSTM cell with the column half of the Winograd output transform folded in: block = (tile row ty, image,
 // 128-channel group), thread = channel, loop over the 10 tiles of the row; per tile and gate the 12 planes
 // t[r][j] = (A2^T m)[r][j] of the GEMM (coalesced 128-byte lines) give the 2 x 4 pre-activations t . A4.
@@ -524,10 +531,10 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
                     }
                     p0 += r0; p1 += r1; p2 += r2;
                 }
-                const float gi = __frcp_rn(1.0f + __expf(-p0));
-                const float gf = __frcp_rn(1.0f + __expf(-p1));
-                const float go = __frcp_rn(1.0f + __expf(-p2));
-                const float gg = 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * p3));
+                const float gi = rcp_approx(1.0f + __expf(-p0));
+                const float gf = rcp_approx(1.0f + __expf(-p1));
+                const float go = rcp_approx(1.0f + __expf(-p2));
+                const float gg = 1.0f - 2.0f * rcp_approx(1.0f + __expf(2.0f * p3));
                 const float cn = gf * cold + gi * gg;
                 c[pix * kE + ch] = cn;
                 __half hh, hl;
