@@ -29,6 +29,26 @@ UNIT = "scanpaths/s"
 T_STEPS, A = 16, 1201
 
 
+_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """Everything libraries print to stdout during the run (NCCL's version banner, ...) goes to stderr, so that
+    the JSON line is the only thing on stdout."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,7 +150,7 @@ def run_reference_arm(args, rank):
             "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args):
@@ -369,11 +389,12 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "scores": {"ScanMatch_wd": m["ScanMatch"]["with duration"], "ScanMatch_wod": m["ScanMatch"]["w/o duration"],
                            "SED": m["VAME"]["SED"], "STDE": m["VAME"]["STDE"]}}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
