@@ -201,6 +201,7 @@ typedef struct spb_decoder_weights {
     const float *bias_p;             /* [n_weight_sets*512]                              */
     const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */
                                      /*   row ((s*3+g)*512+co)*9+tap, col ci             */
+    const void *wm_hi, *wm_lo;       /* the same as an fp16 pair (tensor-core route)     */
     const float *w2, *w3;            /* [512] object_head.sal_layer_2 / sal_layer_3      */
     const float *wd1;                /* [49, 512] object_head.drt_layer_1, tap-major     */
     const float *wd2;                /* [2, 48]   object_head.drt_layer_2                */
@@ -208,6 +209,7 @@ typedef struct spb_decoder_weights {
     const float *b_spatial_embed;    /* [1200] */
     const float *w_semantic_embed;   /* [512, 512] */
     const float *b_semantic_embed;   /* [512] */
+    const void *wse_hi, *wse_lo;     /* w_semantic_embed as an fp16 pair (tensor-core route) */
     /* composed head (tensor-core path): the 5x5 layer feeds sal_layer_2, sal_layer_3 and drt_layer_1
      * with no nonlinearity in between, so they collapse into effective kernels on h:          */
     const void *w23_hi, *w23_lo;     /* fp16 [n_weight_sets*128, 512] 5x5 -> (stop map, action map) as a per-pixel */
@@ -220,10 +222,11 @@ typedef struct spb_decoder_weights {
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;
-    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_wx, inv_scale_23;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_wx, inv_scale_23, inv_scale_m, inv_scale_se;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
     int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
     int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
     int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
+    int32_t reserved;
 } spb_decoder_weights;
 
 typedef struct spb_decoder_io {

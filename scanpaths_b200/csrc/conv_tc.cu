@@ -650,10 +650,13 @@ static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, i
 
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     using namespace tc;
-    // ks = 1 / 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11
+    // ks = 1 / 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11; with ks = 1 an "image" may
+    // be any multiple of 240 rows (plain batched GEMM: out[b][row][col] = sum_k a[b][row][k] w[base_b + col][k])
+    const int rows = a.rows_per_img;
     if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0 ||
-        a.w_row_div < 1) {
-        set_error("conv_gemm_tc: cols must be a multiple of %d, ks 1, 3 or 5, out 16-byte aligned", kTileCh);
+        a.w_row_div < 1 || rows <= 0 || rows % kTilePix != 0 || (a.ks != 1 && rows != kHW)) {
+        set_error("conv_gemm_tc: cols must be a multiple of %d, rows per image of %d, ks 1, 3 or 5, out 16-byte aligned",
+                  kTileCh, kTilePix);
         return SPB_ERR_ARG;
     }
     if (get_encode() == nullptr) {
@@ -662,16 +665,16 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     }
     const int64_t K = (int64_t)a.ks * a.ks * kE;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo;
-    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, kHW);
-    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, kHW);
+    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows);
+    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
-    if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * kHW, kTileCh);
+    if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, kTileCh);
     if (rc) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
     }
-    const int nct = a.cols / kTileCh, pt = kHW / kTilePix;
+    const int nct = a.cols / kTileCh, pt = rows / kTilePix;
     const int64_t tiles64 = (int64_t)nct * pt * a.n_images;
     if (tiles64 > 0x7fffffff) {
         set_error("conv_gemm_tc: too many tiles");
@@ -681,7 +684,7 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
     const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
 #define SPB_LAUNCH_TC(KS_)                                                                                          \
     SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, kHW)
+    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
     if (a.ks == 1) { SPB_LAUNCH_TC(1); }
     else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
     else { SPB_LAUNCH_TC(5); }

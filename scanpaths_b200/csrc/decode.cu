@@ -800,7 +800,8 @@ init_spatial_feat_kernel(const float *__restrict__ att, const float *__restrict_
 // streams and image_stride between images (att: S identical copies via stride 0).
 __global__ void __launch_bounds__(256)
 semantic_feat_kernel(const float *__restrict__ vf, const float *__restrict__ maps, int64_t image_stride,
-                     int64_t stream_stride, int S, float *__restrict__ se_feat, int64_t n_images) {
+                     int64_t stream_stride, int S, float *__restrict__ se_feat, __half *__restrict__ sf_hi,
+                     __half *__restrict__ sf_lo, int64_t n_images) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_images * kE) return;
@@ -820,7 +821,15 @@ semantic_feat_kernel(const float *__restrict__ vf, const float *__restrict__ map
     for (int st = 0; st < S; ++st) {
         float a = s[st];
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) se_feat[(n * S + st) * kE + c] = fmaxf(a / (float)kHW, 0.0f);
+        if (lane == 0) {
+            const float v = fmaxf(a / (float)kHW, 0.0f);
+            se_feat[(n * S + st) * kE + c] = v;
+            if (sf_hi) {                                  // operand of the tensor-core semantic_embed GEMM
+                __half hh, hl;
+                split_one(v, hh, hl);
+                sf_hi[(n * S + st) * kE + c] = hh; sf_lo[(n * S + st) * kE + c] = hl;
+            }
+        }
     }
 }
 
@@ -831,8 +840,8 @@ __global__ void __launch_bounds__(256)
 attention_update_kernel(const float *__restrict__ sp_new, const float *__restrict__ se_new,
                         const float *__restrict__ w_eff, const float *__restrict__ u_sem,
                         float *__restrict__ sp_list, float *__restrict__ se_list, float *__restrict__ sp_score,
-                        float *__restrict__ se_score, float *__restrict__ sp_mem, float *__restrict__ se_mem, int t,
-                        int cap) {
+                        float *__restrict__ se_score, float *__restrict__ sp_mem, float *__restrict__ se_mem,
+                        __half *__restrict__ sm_hi, __half *__restrict__ sm_lo, int S, int64_t sm_rows, int t, int cap) {
     __shared__ float sh[8];
     __shared__ float wsp[32], wse[32];
     const int64_t ns = blockIdx.x;
@@ -871,6 +880,12 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
         float s = 0.0f;
         for (int j = 0; j <= t; ++j) s = fmaf(sel[(int64_t)j * kE + c], wse[j], s);
         se_mem[ns * kE + c] = s;
+        if (sm_hi) {                                      // operand of the tensor-core rank-1 projection: [stream][image][c]
+            __half hh, hl;
+            split_one(s, hh, hl);
+            const int64_t o = ((ns % S) * sm_rows + ns / S) * kE + c;
+            sm_hi[o] = hh; sm_lo[o] = hl;
+        }
     }
 }
 
@@ -881,6 +896,8 @@ struct Workspace {
     int64_t rows_pad;
     float *vfmean, *xg, *c, *acc, *feat, *V, *y2, *y3, *dc, *sp_feat, *se_feat, *sp_new, *se_new, *sp_list, *se_list,
         *sp_score, *se_score, *sp_mem, *se_mem, *drt_pre;
+    __half *sm_hi, *sm_lo, *sf_hi, *sf_lo;   // fp16 pairs of semantic_mem [S][gemm_rows][512] and of the semantic feature [gemm_rows2][512]
+    int64_t gemm_rows, gemm_rows2;           // N resp. N*S rounded up to the GEMM's 240-row tiles
     float *z23;            // composed-head GEMM result [N*1200][HD*128] (aliases feat: the two routes never meet)
     int64_t bytes;
 };
@@ -906,14 +923,20 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.acc = (float *)take(N * kHW * kGateCols * 4);
     w.feat = (float *)take(N * kHW * HD * kE * 4);
     w.z23 = w.feat;
-    w.V = (float *)take(N * S * 3 * kE * 9 * 4);
+    w.gemm_rows = (N + 239) / 240 * 240;
+    w.gemm_rows2 = (N * S + 239) / 240 * 240;
+    w.V = (float *)take(w.gemm_rows * S * 3 * kE * 9 * 4);       // rows >= N are scratch of the tensor-core GEMM
     w.y2 = (float *)take(N * HD * kHW * 4);
     w.y3 = (float *)take(N * HD * kHW * 4);
     w.dc = (float *)take(N * HD * kHW * 16);
     w.sp_feat = (float *)take(N * S * kHW * 4);
     w.se_feat = (float *)take(N * S * kE * 4);
     w.sp_new = (float *)take(N * S * kHW * 4);
-    w.se_new = (float *)take(N * S * kE * 4);
+    w.se_new = (float *)take(w.gemm_rows2 * kE * 4);
+    w.sm_hi = (__half *)take(S * w.gemm_rows * kE * 2);
+    w.sm_lo = (__half *)take(S * w.gemm_rows * kE * 2);
+    w.sf_hi = (__half *)take(w.gemm_rows2 * kE * 2);
+    w.sf_lo = (__half *)take(w.gemm_rows2 * kE * 2);
     w.sp_list = (float *)take(N * S * cap * kHW * 4);
     w.se_list = (float *)take(N * S * cap * kE * 4);
     w.sp_score = (float *)take(N * S * cap * 4);
@@ -1033,11 +1056,19 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         // spatial_embed / semantic_embed (:197-198, :336, :339) then the two memory attentions
         SPB_TRY(sgemm_nt(ws.sp_feat, kHW, w->w_spatial_embed, kHW, w->b_spatial_embed, ws.sp_new, kHW, (int)(N * S),
                          kHW, kHW, s));
-        SPB_TRY(sgemm_nt(ws.se_feat, kE, w->w_semantic_embed, kE, w->b_semantic_embed, ws.se_new, kE, (int)(N * S), kE,
-                         kE, s));
+        if (tc) {
+            ConvGemmArgs a{ws.sf_hi, ws.sf_lo, (const __half *)w->wse_hi, (const __half *)w->wse_lo, nullptr, kE,
+                           w->b_semantic_embed, ws.se_new, kE, 1, kE, 1, w->inv_scale_se};
+            a.rows_per_img = (int)ws.gemm_rows2;
+            SPB_TRY(conv_gemm_tc(a, s));
+        } else {
+            SPB_TRY(sgemm_nt(ws.se_feat, kE, w->w_semantic_embed, kE, w->b_semantic_embed, ws.se_new, kE, (int)(N * S), kE,
+                             kE, s));
+        }
         attention_update_kernel<<<(unsigned)(N * S), 256, 0, s>>>(ws.sp_new, ws.se_new, w->w_eff_spatial, w->u_semantic,
                                                                   ws.sp_list, ws.se_list, ws.sp_score, ws.se_score,
-                                                                  ws.sp_mem, ws.se_mem, list_index, cap);
+                                                                  ws.sp_mem, ws.se_mem, tc ? ws.sm_hi : nullptr, ws.sm_lo, S,
+                                                                  ws.gemm_rows, list_index, cap);
         SPB_LAUNCH_CHECK();
         return SPB_OK;
     };
@@ -1045,8 +1076,12 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     // ---- memories seeded from the attention map (zeros for OSIE) (:333-343)
     init_spatial_feat_kernel<<<(unsigned)((N * S * kHW + 255) / 256), 256, 0, s>>>(io->d_att, ws.vfmean, ws.sp_feat, S, N);
     SPB_LAUNCH_CHECK();
+    SPB_CUDA(cudaMemsetAsync(ws.sm_hi, 0, (size_t)S * ws.gemm_rows * kE * 2, s));     // rows >= N feed scratch outputs only
+    SPB_CUDA(cudaMemsetAsync(ws.sm_lo, 0, (size_t)S * ws.gemm_rows * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.sf_hi, 0, (size_t)ws.gemm_rows2 * kE * 2, s));
+    SPB_CUDA(cudaMemsetAsync(ws.sf_lo, 0, (size_t)ws.gemm_rows2 * kE * 2, s));
     semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(io->d_vf, io->d_att, kHW, 0, S,
-                                                                              ws.se_feat, N);
+                                                                              ws.se_feat, tc ? ws.sf_hi : nullptr, ws.sf_lo, N);
     SPB_LAUNCH_CHECK();
     prof_begin(kTagFeedback, s);
     SPB_TRY(feedback_tail(0));
@@ -1055,9 +1090,19 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     for (int t = 0; t < T; ++t) {
         prof_begin(kTagRank1, s);
         // rank-1 gate projections V[n,s,g,co,tap] = sum_ci W[s,g,co,tap,ci] * semantic_mem[n,s,ci]
-        for (int st = 0; st < S; ++st)
-            SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
-                             ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
+        for (int st = 0; st < S; ++st) {
+            if (tc) {
+                ConvGemmArgs a{ws.sm_hi + st * ws.gemm_rows * kE, ws.sm_lo + st * ws.gemm_rows * kE,
+                               (const __half *)w->wm_hi + (int64_t)st * 3 * kE * 9 * kE,
+                               (const __half *)w->wm_lo + (int64_t)st * 3 * kE * 9 * kE, nullptr, 3 * kE * 9, nullptr,
+                               ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, 1, 3 * kE * 9, 1, w->inv_scale_m};
+                a.rows_per_img = (int)ws.gemm_rows;
+                SPB_TRY(conv_gemm_tc(a, s));
+            } else {
+                SPB_TRY(sgemm_nt(ws.se_mem + st * kE, (int64_t)S * kE, w->wm + (int64_t)st * 3 * kE * 9 * kE, kE, nullptr,
+                                 ws.V + (int64_t)st * 3 * kE * 9, (int64_t)S * 3 * kE * 9, (int)N, 3 * kE * 9, kE, s));
+            }
+        }
         prof_end(s);
         const int cur = t & 1, nxt = cur ^ 1;
         if (wino) {
@@ -1150,7 +1195,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             // semantic feedback from this step's action map(s): map of (head hd, image n) lives at
             // d_action_map[((hd*N + n)*T + t)*1200]
             semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(
-                io->d_vf, io->d_action_map + (int64_t)t * kHW, (int64_t)T * kHW, N * (int64_t)T * kHW, S, ws.se_feat, N);
+                io->d_vf, io->d_action_map + (int64_t)t * kHW, (int64_t)T * kHW, N * (int64_t)T * kHW, S, ws.se_feat,
+                tc ? ws.sf_hi : nullptr, ws.sf_lo, N);
             SPB_LAUNCH_CHECK();
             SPB_TRY(feedback_tail(t + 1));
             prof_end(s);

@@ -26,6 +26,7 @@ struct ConvGemmArgs {
     int n_images, cols, ks;
     float inv_scale;
     int w_row_div = 1;            // w_row_base is given in units of w_row_div rows
+    int rows_per_img = kHW;       // ks = 1 only: any multiple of 240 (the kernel as a plain batched GEMM)
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].

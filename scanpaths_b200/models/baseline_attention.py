@@ -103,6 +103,7 @@ def prepare_weights(sd, task: str, device):
     wm = [f("lstm.%s%s.weight" % (g, s)).permute(0, 2, 3, 1).reshape(512, 9, 512)
           for s in streams for g in ("input", "forget", "output")]
     t["wm"] = torch.stack(wm, 0).reshape(-1, 512).contiguous()
+    t["wm_hi"], t["wm_lo"], ism = split_pair(t["wm"])
     t["w2"] = f("object_head.sal_layer_2.weight").reshape(512).contiguous()
     t["w3"] = f("object_head.sal_layer_3.weight").reshape(512).contiguous()
     t["wd1"] = f("object_head.drt_layer_1.weight")[0].permute(1, 2, 0).reshape(49, 512).contiguous()
@@ -110,6 +111,7 @@ def prepare_weights(sd, task: str, device):
     t["w_spatial_embed"] = f("spatial_embed.weight").contiguous()
     t["b_spatial_embed"] = f("spatial_embed.bias").contiguous()
     t["w_semantic_embed"] = f("semantic_embed.weight").contiguous()
+    t["wse_hi"], t["wse_lo"], isse = split_pair(t["w_semantic_embed"])
     t["b_semantic_embed"] = f("semantic_embed.bias").contiguous()
     # composed head: feat = conv5x5(h) + bp is consumed only by linear maps (sal_layer_2, sal_layer_3 1x1,
     # drt_layer_1 7x7 stride 5) before any nonlinearity (predict_head.forward :144-150), so
@@ -161,6 +163,7 @@ def prepare_weights(sd, task: str, device):
     bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
     w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
     w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w, w.inv_scale_wx, w.inv_scale_23 = isx, ish, isp, isw, iswx, is23
+    w.inv_scale_m, w.inv_scale_se = ism, isse
     w.n_streams = w.n_heads = len(streams)
     w.n_weight_sets = len(sets)
     return t, w
