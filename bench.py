@@ -321,7 +321,7 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     names = {1: "conv3x3_x", 2: "winograd_gemm_h", 3: "conv5x5", 4: "lstm_cell", 5: "head", 6: "feedback",
-             7: "rank1", 8: "prep", 9: "wino_input"}
+             7: "rank1", 8: "prep", 9: "wino_input", 10: "score_pairs", 11: "sample"}
     share = {names[k]: float(ms_buf[tag_buf == k].sum()) for k in names if (tag_buf == k).any()}
     tot_tagged = sum(share.values()) or 1.0
     conv_h = ms_buf[tag_buf == 2]
@@ -349,6 +349,38 @@ def main():
                             "for fp32-equivalent results, so frac tops out at 1/3; the same convolution done directly "
                             "would need %.2f TFLOP" % (flop_gemm / 1e12, flop_direct / 1e12),
                     "time_share_of_tagged_kernels": {k: v / tot_tagged for k, v in share.items()}}
+
+    # ---- scoring kernel: DP cell-updates/s and HBM GB/s (north_star), from the live brackets of score_pairs_kernel
+    scoring = None
+    score_ms = ms_buf[tag_buf == 10]
+    if len(score_ms):
+        from scanpaths_b200 import scoring as SC
+        w_n = min(args.wave, N)
+        o2 = pipe.run(vf_dev[:w_n], None if att_dev is None else att_dev[:w_n],
+                      None if tasks_dev is None else tasks_dev[:w_n], keep_paths=True)
+        cells = 0.0
+        nbytes = 0.0
+        for (hd, n0, n1, smp) in o2["paths"]:
+            pp = SC.prep_paths(smp["xyd"], smp["len"], pipe.cfg)
+            ph, ps = pipe._pair_map(n1 - n0, n0)
+            lh, lp = pipe.humans.len[ph.long()].double(), pp.len[ps.long()].double()
+            mn = torch.minimum(lh, lp)
+            stde = mn * (lp + 1) * (lh + 1) - (lp + lh + 2) * mn * (mn + 1) / 2 + mn * (mn + 1) * (2 * mn + 1) / 6
+            cells += float((pipe.humans.nwd[ph.long()].double() * pp.nwd[ps.long()].double() + 2 * lh * lp + stde).sum())
+            # unique bytes: both symbol packs (25 B per fixation slot + 8 B per path), pair map, scores
+            nbytes += (pp.len.numel() + (n1 - n0) * S) * (16 * 25 + 8) + ph.numel() * (8 + 32)
+        per_launch = cells / len(o2["paths"])
+        avg_ms = float(score_ms.mean())
+        ach = per_launch / (avg_ms * 1e-3)
+        # ncu (profiles/r01_score_pairs_ncu.txt): 4.06 warp instructions per cell update, 16 of 32 lanes active
+        # (wavefront ramps of ~50-symbol strings); issue peak = 148 SMs x 4 warp-instr/clk x 1.965 GHz / 4.06
+        peak = 148 * 4 * 1.965e9 / 4.06
+        scoring = {"kernel": "score_pairs_kernel", "bound": "sm_issue", "achieved": ach, "peak": peak,
+                   "unit": "DP cell-updates/s", "frac": ach / peak, "avg_launch_ms": avg_ms,
+                   "cell_updates_per_pair": per_launch / (w_n * K * S),
+                   "hbm_gb_s": nbytes / len(o2["paths"]) / (avg_ms * 1e-3) / 1e9,
+                   "hbm_frac": nbytes / len(o2["paths"]) / (avg_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6541.5)),
+                   "note": "cell updates = n_wd*m_wd + 2*Lh*Lp + sum_k (Lp-k+1)(Lh-k+1) per pair, counted on one wave"}
 
     # ---- e2e: host buffers in, host results out, copies inside the timed region
     e2e = None
@@ -386,7 +418,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "config": workload_config(args), "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
-                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "roofline": roofline, "scoring_roofline": scoring, "cpu_baseline": cpu_baseline,
                 "scores": {"ScanMatch_wd": m["ScanMatch"]["with duration"], "ScanMatch_wod": m["ScanMatch"]["w/o duration"],
                            "SED": m["VAME"]["SED"], "STDE": m["VAME"]["STDE"]}}
         _emit(line)

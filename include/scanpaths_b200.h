@@ -44,7 +44,8 @@ int64_t spb_kernel_launches(void);
 
 /* Live profiling for bench.py's roofline: with max_pairs > 0 the decode path brackets its
  * tagged launches (1 = x-conv, 2 = 3x3 gate conv, 3 = 5x5 conv, 4 = LSTM cell, 5 = head,
- * 6 = feedback + attention, 7 = rank-1 projection, 8 = operand prep) with CUDA events on the
+ * 6 = feedback + attention, 7 = rank-1 projection, 8 = operand prep, 9 = Winograd input transform,
+ * 10 = score_pairs kernel, 11 = sampling kernel) with CUDA events on the
  * launching stream; spb_profile_collect waits for them and returns (milliseconds, tag) per
  * bracket, then resets.  max_pairs = 0 turns it off. */
 int spb_profile_enable(int32_t max_pairs);

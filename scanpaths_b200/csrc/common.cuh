@@ -12,7 +12,7 @@ void set_error(const char *fmt, ...);
 void count_launch();
 // optional live profiling: CUDA-event pairs around tagged launches (see spb_profile_enable)
 enum ProfTag { kTagConvX = 1, kTagConvH = 2, kTagConvP = 3, kTagCell = 4, kTagHead = 5, kTagFeedback = 6, kTagRank1 = 7,
-               kTagPrep = 8, kTagWinoIn = 9 };
+               kTagPrep = 8, kTagWinoIn = 9, kTagScore = 10, kTagSample = 11 };
 void prof_begin(int tag, cudaStream_t s);
 void prof_end(cudaStream_t s);
 

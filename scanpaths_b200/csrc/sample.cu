@@ -180,9 +180,11 @@ extern "C" int spb_sample_paths(const float *d_probs, const float *d_mu, const f
     const int64_t cap = (int64_t)spb::kNumSMs * 8;
     if (blocks > cap) blocks = cap;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    spb::prof_begin(spb::kTagSample, s);
     spb::sample_actions_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_probs, d_mu, d_sigma2, d_q, d_z, key, N, T, A, K,
                                                                  geom->min_length, d_actions, d_sel_prob, d_dur);
     SPB_LAUNCH_CHECK();
+    spb::prof_end(s);
     const int64_t ns = (int64_t)K * N;
     int64_t fb = (ns + 255) / 256;
     if (fb > cap) fb = cap;

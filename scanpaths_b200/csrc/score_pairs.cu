@@ -431,10 +431,12 @@ extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *
         ws_per_warp = workspace_bytes / 8 / (blocks * spb::kWarpsPerBlock);
         ws_per_warp &= ~(int64_t)1;
     }
+    spb::prof_begin(spb::kTagScore, (cudaStream_t)stream);
     spb::score_pairs_kernel<<<(unsigned)blocks, spb::kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         *human, *sim, d_pair_h, d_pair_s, n_pairs, *cfg, d_scores, ws_per_warp > 0 ? (double *)d_workspace : nullptr,
         ws_per_warp, d_err);
     SPB_LAUNCH_CHECK();
+    spb::prof_end((cudaStream_t)stream);
     return SPB_OK;
 }
 

@@ -26,5 +26,8 @@ for it in range(4):
     e4 = ev(); torch.cuda.synchronize()
     print('iter', it, 'sample %.2f ms prep %.2f ms score %.2f ms reduce %.2f ms' % (e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e3.elapsed_time(e4)))
 lens = out['len'].float(); print('pred len mean', lens.mean().item(), 'nwd pred mean', pp.nwd.float().mean().item(), 'nwd human mean', hp.nwd.float().mean().item())
-cells = (hp.nwd[ph.long()].double() * pp.nwd[ps.long()].double() + 2 * hp.len[ph.long()].double() * pp.len[ps.long()].double()).sum().item()
-print('pairs', ph.numel(), 'cells(wd+wod+sed) %.3e' % cells, 'mean scores', sc.nanmean(0).tolist())
+lh, lp = hp.len[ph.long()].double(), pp.len[ps.long()].double()
+m = torch.minimum(lh, lp)
+stde = m * (lp + 1) * (lh + 1) - (lp + lh + 2) * m * (m + 1) / 2 + m * (m + 1) * (2 * m + 1) / 6
+cells = (hp.nwd[ph.long()].double() * pp.nwd[ps.long()].double() + 2 * lh * lp + stde).sum().item()
+print('pairs', ph.numel(), 'cell updates (wd + wod + sed + stde windows) %.4e' % cells, 'mean scores', sc.nanmean(0).tolist())
