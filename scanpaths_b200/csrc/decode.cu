@@ -31,16 +31,7 @@ __device__ __forceinline__ void split_one(float v, __half &hi, __half &lo) {
     lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
 }
 
-// the exact fp32 value of an fp16 (hi, lo) pair, 4 / 8 consecutive channels
-__device__ __forceinline__ void load_h4(const __half *hi, const __half *lo, int64_t off, float (&v)[4]) {
-    const uint2 a = *reinterpret_cast<const uint2 *>(hi + off), b = *reinterpret_cast<const uint2 *>(lo + off);
-    const __half2 a0 = *reinterpret_cast<const __half2 *>(&a.x), a1 = *reinterpret_cast<const __half2 *>(&a.y);
-    const __half2 b0 = *reinterpret_cast<const __half2 *>(&b.x), b1 = *reinterpret_cast<const __half2 *>(&b.y);
-    const float2 fa0 = __half22float2(a0), fa1 = __half22float2(a1), fb0 = __half22float2(b0), fb1 = __half22float2(b1);
-    v[0] = fa0.x + fb0.x * (1.0f / kLoScale); v[1] = fa0.y + fb0.y * (1.0f / kLoScale);
-    v[2] = fa1.x + fb1.x * (1.0f / kLoScale); v[3] = fa1.y + fb1.y * (1.0f / kLoScale);
-}
-
+// the exact fp32 value of an fp16 (hi, lo) pair, 8 consecutive channels
 __device__ __forceinline__ void load_h8(const __half *hi, const __half *lo, int64_t off, float (&v)[8]) {
     const uint4 a = *reinterpret_cast<const uint4 *>(hi + off), b = *reinterpret_cast<const uint4 *>(lo + off);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
