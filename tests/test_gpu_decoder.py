@@ -198,3 +198,26 @@ def test_decode_other_seeds_and_feature_scales(lib, seed, scale):
         err = float((np.abs(probs[0].double().cpu().numpy() - p64) / p64).max())
         print("seed %d scale %.2f mode %d: %.2e (float32 reference: %.2e)" % (seed, scale, mode, err, ref_err))
         assert err < bound, (mode, err, ref_err)
+
+
+def test_decode_full_wave_is_independent_of_batch_layout(lib):
+    """BASELINE-size property (one full wave of 256 images): an image's result does not depend on where
+    it sits in the wave -- Winograd GEMM tiles of 128 rows straddle image boundaries (150 tiles per
+    image), so a permuted wave exercises every row-block / image alignment.  Bit-exact."""
+    from scanpaths_b200.models.baseline_attention import CudaDecoder
+    from scanpaths_b200.weights import random_state_dict
+    dev = torch.device("cuda")
+    N, T = 256, 3
+    sd = random_state_dict("OSIE", 5, calibrated=True, bias_std=0.05)
+    g = torch.Generator(device=dev).manual_seed(21)
+    vf = torch.randn((N, 512, 30, 40), generator=g, device=dev).clamp_min_(0)
+    dec = CudaDecoder(sd, "OSIE", T, dev, wave=N)
+    p0, m0, s0, a0 = [x.clone() for x in dec.decode(vf)]
+    perm = torch.randperm(N, generator=g, device=dev)
+    p1, m1, s1, a1 = dec.decode(vf[perm].contiguous())
+    assert torch.equal(p1, p0[:, perm]) and torch.equal(m1, m0[:, perm]) and torch.equal(s1, s0[:, perm])
+    assert torch.equal(a1, a0[:, perm])
+    assert torch.isfinite(p0).all() and abs(float(p0.sum(-1).mean()) - 1.0) < 1e-5
+    # and a partial wave (pad rows of the GEMM row blocks) equals the head of the full one
+    p2, m2, s2, a2 = dec.decode(vf[:37].contiguous())
+    assert torch.equal(p2, p0[:, :37]) and torch.equal(m2, m0[:, :37])
