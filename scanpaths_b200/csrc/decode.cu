@@ -183,12 +183,19 @@ int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s) {
 // C[M,N] = A[M,K] * B[N,K]^T + bias[N]   (fp32 SIMT; the small per-step GEMMs:
 // spatial_embed, semantic_embed, rank-1 gate projection)
 // ---------------------------------------------------------------------------
+// Split-K: blockIdx.z owns the k-range [z*k_chunk, min(K, (z+1)*k_chunk)) and writes its partial sums to
+// C + z*c_split_stride (bias added by slice 0); the consumer adds the slices.
 __global__ void __launch_bounds__(256, 6)
 sgemm_nt_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
-                const float *__restrict__ bias, float *__restrict__ C, int64_t ldc, int M, int N, int K) {
+                const float *__restrict__ bias, float *__restrict__ C, int64_t ldc, int M, int N, int K, int k_chunk,
+                int64_t c_split_stride) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    A += (int64_t)blockIdx.z * k_chunk; B += (int64_t)blockIdx.z * k_chunk;
+    C += (int64_t)blockIdx.z * c_split_stride;
+    K = min(K - (int)blockIdx.z * k_chunk, k_chunk);
+    if (blockIdx.z > 0) bias = nullptr;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int lr = tid >> 2, lk = (tid & 3) * 4;
     float acc[4][4] = {};
@@ -222,9 +229,10 @@ sgemm_nt_kernel(const float *__restrict__ A, int64_t lda, const float *__restric
 }
 
 static int sgemm_nt(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias, float *C, int64_t ldc,
-                    int M, int N, int K, cudaStream_t s) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_nt_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+                    int M, int N, int K, cudaStream_t s, int splits = 1, int64_t c_split_stride = 0) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    const int k_chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    sgemm_nt_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, k_chunk, c_split_stride);
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }
@@ -832,14 +840,16 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
                         const float *__restrict__ w_eff, const float *__restrict__ u_sem,
                         float *__restrict__ sp_list, float *__restrict__ se_list, float *__restrict__ sp_score,
                         float *__restrict__ se_score, float *__restrict__ sp_mem, float *__restrict__ se_mem,
-                        __half *__restrict__ sm_hi, __half *__restrict__ sm_lo, int S, int64_t sm_rows, int t, int cap) {
+                        __half *__restrict__ sm_hi, __half *__restrict__ sm_lo, int S, int64_t sm_rows, int t, int cap,
+                        int sp_splits, int64_t sp_split_stride) {
     __shared__ float sh[8];
     __shared__ float wsp[32], wse[32];
     const int64_t ns = blockIdx.x;
     float *spl = sp_list + ns * (int64_t)cap * kHW, *sel = se_list + ns * (int64_t)cap * kE;
     float a = 0.0f, b = 0.0f;
     for (int p = threadIdx.x; p < kHW; p += blockDim.x) {
-        const float v = sp_new[ns * kHW + p];
+        float v = sp_new[ns * kHW + p];
+        for (int z = 1; z < sp_splits; ++z) v += sp_new[z * sp_split_stride + ns * kHW + p];   // split-K slices of spatial_embed
         spl[(int64_t)t * kHW + p] = v;
         a = fmaf(v, w_eff[p], a);
     }
@@ -881,6 +891,8 @@ attention_update_kernel(const float *__restrict__ sp_new, const float *__restric
 }
 
 // ---------------------------------------------------------------------------
+constexpr int kSpSplits = 4;     // split-K slices of the spatial_embed GEMM
+
 struct Workspace {
     __half *vf_hi, *vf_lo, *h_hi[2], *h_lo[2], *u_hi, *u_lo;
     float *wm;             // Winograd GEMM results after the row transform, tile-major [12][2048/128][rows_pad][128]
@@ -922,7 +934,7 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.dc = (float *)take(N * HD * kHW * 16);
     w.sp_feat = (float *)take(N * S * kHW * 4);
     w.se_feat = (float *)take(N * S * kE * 4);
-    w.sp_new = (float *)take(N * S * kHW * 4);
+    w.sp_new = (float *)take(kSpSplits * N * S * kHW * 4);
     w.se_new = (float *)take(w.gemm_rows2 * kE * 4);
     w.sm_hi = (__half *)take(S * w.gemm_rows * kE * 2);
     w.sm_lo = (__half *)take(S * w.gemm_rows * kE * 2);
@@ -1045,8 +1057,10 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
 
     auto feedback_tail = [&](int list_index) -> int {
         // spatial_embed / semantic_embed (:197-198, :336, :339) then the two memory attentions
+        // spatial_embed: K = 1200 over only 76 output tiles -> split-K so that all SMs work; the slices are
+        // summed by attention_update_kernel
         SPB_TRY(sgemm_nt(ws.sp_feat, kHW, w->w_spatial_embed, kHW, w->b_spatial_embed, ws.sp_new, kHW, (int)(N * S),
-                         kHW, kHW, s));
+                         kHW, kHW, s, kSpSplits, N * S * kHW));
         if (tc) {
             ConvGemmArgs a{ws.sf_hi, ws.sf_lo, (const __half *)w->wse_hi, (const __half *)w->wse_lo, nullptr, kE,
                            w->b_semantic_embed, ws.se_new, kE, 1, kE, 1, w->inv_scale_se};
@@ -1059,7 +1073,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         attention_update_kernel<<<(unsigned)(N * S), 256, 0, s>>>(ws.sp_new, ws.se_new, w->w_eff_spatial, w->u_semantic,
                                                                   ws.sp_list, ws.se_list, ws.sp_score, ws.se_score,
                                                                   ws.sp_mem, ws.se_mem, tc ? ws.sm_hi : nullptr, ws.sm_lo, S,
-                                                                  ws.gemm_rows, list_index, cap);
+                                                                  ws.gemm_rows, list_index, cap, kSpSplits,
+                                                                  N * S * kHW);
         SPB_LAUNCH_CHECK();
         return SPB_OK;
     };
