@@ -63,7 +63,8 @@ def parse():
                     help="model variant of the workload (default: the OSIE-shaped configs[1] the metric is quoted on)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=2, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=16,
+                    help="images in the bounded CPU-baseline sample (about 10-15 s on 16 cores)")
     return ap.parse_args()
 
 
@@ -133,7 +134,7 @@ def run_reference_arm(args, rank):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_img = 1
+    n_img = 8                                             # bounded sample per step: ~5 s on 16 cores
     with mp.get_context("fork").Pool(cores) as pool:
         for i in range(args.warmup):
             cpu_port_step(n_img, args.samples, args.subjects, 100 + i, pool)
