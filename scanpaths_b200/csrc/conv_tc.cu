@@ -310,9 +310,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         uint32_t v[8];
                         tmem_ld8(lane_addr + c, v);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) tot[c + j] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 8; ++j) tot[c + j] = __uint_as_float(v[j]);     // (bias fix applied below)
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < kHalfPix; ++c) tot[c] = fmaf(tot[c], kAccTruncFix, tot[c]);
                 } else {
 #pragma unroll
                     for (int c = 0; c < kHalfPix; c += 24) {
@@ -323,9 +325,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            tot[c + j] += __uint_as_float(v0[j]);
-                            tot[c + 8 + j] += __uint_as_float(v1[j]);
-                            tot[c + 16 + j] += __uint_as_float(v2[j]);
+                            const float x0 = __uint_as_float(v0[j]), x1 = __uint_as_float(v1[j]), x2 = __uint_as_float(v2[j]);
+                            tot[c + j] += fmaf(x0, kAccTruncFix, x0);
+                            tot[c + 8 + j] += fmaf(x1, kAccTruncFix, x1);
+                            tot[c + 16 + j] += fmaf(x2, kAccTruncFix, x2);
                         }
                     }
                 }
@@ -564,7 +567,8 @@ wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_con
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, __uint_as_float(vm[e >> 3][e & 7]));
+                        const float mm = __uint_as_float(vm[e >> 3][e & 7]);
+                        const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, fmaf(mm, kAccTruncFix, mm));
                         if (i == 0) sa[c + e] = m;
                         else if (i == 1) { sa[c + e] += m; sb[c + e] = m; }
                         else if (i == 2) { sa[c + e] += m; sb[c + e] -= m; }

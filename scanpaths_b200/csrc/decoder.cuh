@@ -10,6 +10,13 @@ constexpr int kE = 512;          // embedding channels
 constexpr int kH = 30, kW = 40, kHW = 1200;
 constexpr int kGateCols = 4 * kE;   // i, f, o, g
 constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
+// The tensor core adds into its fp32 accumulator with truncation toward zero.  Over the 32 k-steps a
+// "main" accumulator lives (one filter tap / one Winograd position) that shrinks the result by a factor
+// measured on B200 as 1 - 5.5e-7 (scratch/bias_probe.py: -5.36e-7 .. -5.52e-7 for every kernel of this file
+// and every input distribution with mixed-sign weights; -2.6e-6 if all terms have one sign).  Unlike
+// rounding noise this bias is coherent over all outputs and steps -- it made the decode error grow linearly
+// with the step count -- so the drain warps multiply it back: x += x * kAccTruncFix.
+constexpr float kAccTruncFix = 5.5e-7f;
 
 // One implicit-GEMM convolution:  out[(n*1200+p)*ldo + col] = inv_scale * conv(a, w)[p, col] (+ bias[col])
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]

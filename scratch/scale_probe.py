@@ -5,10 +5,10 @@ from scanpaths_b200.weights import random_state_dict, synthetic_features
 from oracle import decoder as OD
 torch.set_num_threads(16)
 dev = torch.device('cuda')
-for seed, scale in ((12, 4.0), (12, 1.0)):
+for seed, scale in ((12, 4.0), (12, 2.0), (12, 1.0)):
     sd = random_state_dict('OSIE', seed, calibrated=True, bias_std=0.05)
     vf = synthetic_features(1, seed) * scale
-    T = 8
+    T = 16
     with torch.no_grad():
         ref = OD.decode(sd, vf.double(), 'OSIE', steps=T)
         ref32 = OD.decode(sd, vf.float(), 'OSIE', steps=T)

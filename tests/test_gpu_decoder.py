@@ -44,7 +44,7 @@ def test_wino_gemm_row_transform(lib):
     ref = torch.stack([m[:, 0] + m[:, 1] + m[:, 2], m[:, 1] - m[:, 2] - m[:, 3]], 1).reshape(12, rows, cols)
     got = out.permute(0, 2, 1, 3).reshape(12, rows, cols)
     err = (got.double() - ref).abs().max().item()
-    assert err < 2e-6 * m.abs().max().item(), err       # 32 truncating accumulation steps on the leading products
+    assert err < 1e-6 * m.abs().max().item(), err       # 32 truncating accumulation steps, bias multiplied back
 
 
 def _conv_case(lib, ks, n_images, cols, use_tc, per_image_sets=0, seed=0):
