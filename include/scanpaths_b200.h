@@ -213,8 +213,9 @@ typedef struct spb_decoder_weights {
     const void *wse_hi, *wse_lo;     /* w_semantic_embed as an fp16 pair (tensor-core route) */
     /* composed head (tensor-core path): the 5x5 layer feeds sal_layer_2, sal_layer_3 and drt_layer_1
      * with no nonlinearity in between, so they collapse into effective kernels on h:          */
-    const void *w23_hi, *w23_lo;     /* fp16 [n_weight_sets*128, 512] 5x5 -> (stop map, action map) as a per-pixel */
-                                     /*   GEMM: row = tap*2 + map (rows 50..127 zero)                          */
+    const void *w23_hi, *w23_lo;     /* fp16 [n_weight_sets*256, 512] the head as a per-pixel GEMM: rows [0,50) =  */
+                                     /*   tap*2 + map of the 5x5 -> (stop map, action map), rows [128,249) = the  */
+                                     /*   121 taps of wd_eff variant 0, the rest zero                             */
     const float *b23_eff;            /* [n_weight_sets, 2]  incl. sal_layer_2/3 bias             */
     const float *wd_eff;             /* [n_weight_sets, 4, 121, 512] 11x11 stride-5 duration conv; variant = */
                                      /*   2*(window in top row) + (window in left column): taps of drt_layer_1 */

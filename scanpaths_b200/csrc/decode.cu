@@ -631,11 +631,14 @@ head_reduce_kernel(const float *__restrict__ feat, int HD, const float *__restri
 // with effective kernels composed once in float64 (prepare_weights).  h is read as the same fp16
 // (hi, lo) pair the gate GEMM consumes.
 // The 5x5 -> 2 convolution runs as a per-pixel GEMM on the tensor cores: Z[p][tap*2 + map] = h[p,:] . w23[tap,map,:]
-// (conv_gemm_tc with ks = 1: 128 weight rows per head, 50 used; h is read once) followed by the 25-tap
+// (conv_gemm_tc with ks = 1: 256 weight rows per head; h is read once) followed by the 25-tap
 // gather below, y[p] = sum_tap Z[p + tap][tap] -- the direct SIMT form of this convolution was FMA-bound
-// at 0.77 ms per 256-image step.
+// at 0.77 ms per 256-image step.  The same GEMM carries the 121 taps of the duration convolution (rows 128..248:
+// the interior variant, 35 of the 48 windows), gathered by head_drt_gather_kernel.
 // ---------------------------------------------------------------------------
-constexpr int kHeadCols = 128;       // GEMM columns (weight rows) per head: 25 taps x 2 maps, zero-padded
+constexpr int kHeadCols = 256;       // GEMM columns (weight rows) per head: [0,50) = 25 taps x 2 maps, [128,249) = the 121 taps of the
+                                     // duration convolution (interior variant), the rest zero
+constexpr int kDrtCol0 = 128;
 
 // one thread per (image, head, pixel): 25 float2 loads from Z (L2-resident), zero padding by bounds
 __global__ void __launch_bounds__(256)
@@ -667,7 +670,7 @@ head_gather_kernel(const float *__restrict__ z, int ldz, const float *__restrict
     y3[idx] = s3 + b23[set * 2 + 1];
 }
 
-// duration pre-activation of the 48 windows: one 4-warp block per (image, head, window); the 121
+// duration pre-activation of the border windows: one 4-warp block per (image, head, window); the 121
 // taps are dealt round-robin to the warps, lanes split the channels, partial sums meet in smem.
 __global__ void __launch_bounds__(128)
 head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ wd_eff,
@@ -675,9 +678,12 @@ head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo
                 float *__restrict__ drt_pre) {
     __shared__ float part[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t win = blockIdx.x;                   // (n*HD + hd)*48 + o
-    const int o = (int)(win % 48);
-    const int64_t nh = win / 48;
+    // only the 13 windows of the top row / left column run here (their composed kernels differ: 3 border
+    // variants); the 35 interior windows are gathered from the head GEMM by head_drt_gather_kernel
+    const int bi = (int)(blockIdx.x % 13);
+    const int o = bi < 8 ? bi : (bi - 7) * 8;
+    const int64_t nh = blockIdx.x / 13;
+    const int64_t win = nh * 48 + o;                  // (n*HD + hd)*48 + o
     const int64_t n = nh / HD;
     const int hd = (int)(nh % HD);
     const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
@@ -705,6 +711,35 @@ head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo
     if (lane == 0) part[warp] = acc;
     __syncthreads();
     if (threadIdx.x == 0) drt_pre[win] = ((part[0] + part[1]) + (part[2] + part[3])) + bd_eff[set * 4 + variant];
+}
+
+// duration pre-activation of the 35 interior windows from the head GEMM: Z[p][kDrtCol0 + tap] = h[p,:] . wd_eff[set][0][tap,:],
+// drt[o] = sum over the window's 11 x 11 pixels of Z[p][tap(p)] (pixels below / right of the image are padding).
+// One warp per (image, head, interior window).
+__global__ void __launch_bounds__(256)
+head_drt_gather_kernel(const float *__restrict__ z, int ldz, const float *__restrict__ bd_eff,
+                       const int32_t *__restrict__ w_row_base, int HD, float *__restrict__ drt_pre, int64_t n_warps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_warps) return;
+    const int wi = (int)(w % 35);
+    const int64_t nh = w / 35;
+    const int64_t n = nh / HD;
+    const int hd = (int)(nh % HD);
+    const int oy = 1 + wi / 7, ox = 1 + wi % 7;
+    const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
+    const float *zb = z + n * kHW * (int64_t)ldz + hd * kHeadCols + kDrtCol0;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int tap = lane + 32 * q;
+        const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
+        const bool in = tap < 121 && yy < kH && xx < kW;           // interior windows never reach above / left of the image
+        v[q] = in ? __ldg(zb + (int64_t)(yy * kW + xx) * ldz + tap) : 0.0f;
+    }
+    float acc = (v[0] + v[1]) + (v[2] + v[3]);
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) drt_pre[nh * 48 + oy * 8 + ox] = acc + bd_eff[set * 4];
 }
 
 __device__ __forceinline__ float block_reduce(float v, float *sh, bool is_max) {
@@ -1173,8 +1208,11 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             head_gather_kernel<<<(unsigned)((N * HD * kHW + 255) / 256), 256, 0, s>>>(
                 ws.z23, HD * kHeadCols, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3, N * HD * kHW);
             SPB_LAUNCH_CHECK();
-            head_drt_kernel<<<(unsigned)(N * HD * 48), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
+            head_drt_kernel<<<(unsigned)(N * HD * 13), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
                                                                    io->d_w_row_base, HD, ws.drt_pre);
+            SPB_LAUNCH_CHECK();
+            head_drt_gather_kernel<<<(unsigned)((N * HD * 35 * 32 + 255) / 256), 256, 0, s>>>(
+                ws.z23, HD * kHeadCols, w->bd_eff, io->d_w_row_base, HD, ws.drt_pre, N * HD * 35);
             SPB_LAUNCH_CHECK();
         } else {
             // verification path: the explicit 5x5 layer(s), then the three head convolutions on feat

@@ -125,10 +125,6 @@ def prepare_weights(sd, task: str, device):
     w3_64 = f("object_head.sal_layer_3.weight").double().reshape(512)
     wd_64 = f("object_head.drt_layer_1.weight").double()[0]                      # [c, 7, 7]
     w23 = torch.stack([torch.einsum("c,scikl->skli", w2_64, wp64), torch.einsum("c,scikl->skli", w3_64, wp64)], -1)
-    # as rows of a per-pixel GEMM: [set][tap*2 + map][ci], zero-padded to 128 rows per set
-    w23g = torch.zeros((len(sets), 128, 512), dtype=torch.float64, device=device)
-    w23g[:, :50] = w23.reshape(len(sets), 25, 512, 2).permute(0, 1, 3, 2).reshape(len(sets), 50, 512)
-    t["w23_hi"], t["w23_lo"], is23 = split_pair(w23g.reshape(len(sets) * 128, 512))
     b23 = torch.stack([bp64 @ w2_64 + f("object_head.sal_layer_2.bias").double()[0],
                        bp64 @ w3_64 + f("object_head.sal_layer_3.bias").double()[0]], -1)
     t["b23_eff"] = b23.float().contiguous()
@@ -145,6 +141,12 @@ def prepare_weights(sd, task: str, device):
             wde.append(comp.permute(0, 2, 3, 1).reshape(len(sets), 121, 512))
             bde.append(bp64 @ m.sum(dim=(1, 2)) + f("object_head.drt_layer_1.bias").double()[0])
     t["wd_eff"] = torch.stack(wde, 1).float().contiguous()                       # [sets, 4, 121, 512]
+    # the head as rows of a per-pixel GEMM, 256 rows per set: [0, 50) = (tap*2 + map) of the 5x5 -> 2 maps,
+    # [128, 249) = the 121 taps of the interior variant of the duration convolution, the rest zero
+    w23g = torch.zeros((len(sets), 256, 512), dtype=torch.float64, device=device)
+    w23g[:, :50] = w23.reshape(len(sets), 25, 512, 2).permute(0, 1, 3, 2).reshape(len(sets), 50, 512)
+    w23g[:, 128:249] = wde[0]
+    t["w23_hi"], t["w23_lo"], is23 = split_pair(w23g.reshape(len(sets) * 256, 512))
     t["bd_eff"] = torch.stack(bde, 1).float().contiguous()                       # [sets, 4]
     # spatial_att: score_j = <spatial_attention, conv3x3(spatial_lists, list_j)> + const
     #            = <w_eff, list_j> + const  (adjoint of the 3x3 correlation applied to spatial_attention)
