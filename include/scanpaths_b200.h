@@ -197,7 +197,6 @@ typedef struct spb_decoder_weights {
     const void *ww_hi, *ww_lo;       /* fp16 [24*2048, 512] Winograd F(2x4,3x3)-transformed lstm.*_h: G2 g G4^T,     */
                                      /*   position-major, position = 4*(column position j) + (row position i)   */
     const void *wwx_hi, *wwx_lo;     /* the same for lstm.*_x (the loop-invariant x-gate convolution)              */
-    const int32_t *d_wino_row_base;  /* [24] = position * 2048                          */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
     const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */

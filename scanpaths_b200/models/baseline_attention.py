@@ -87,7 +87,6 @@ def prepare_weights(sd, task: str, device):
         return _interleave_gates(mats).view(2048, 24, 512).permute(1, 0, 2).reshape(24 * 2048, 512)
     t["ww_hi"], t["ww_lo"], isw = split_pair(wino_rows(GATES_H))
     t["wwx_hi"], t["wwx_lo"], iswx = split_pair(wino_rows(GATES_X))
-    t["d_wino_row_base"] = (torch.arange(24, device=device, dtype=torch.int32) * 2048).contiguous()
     t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
     t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
     t["wp_hi"], t["wp_lo"], isp = split_pair(wp)
