@@ -79,6 +79,8 @@ typedef struct spb_score_cfg {
     const double *d_sub_delta;     /* device copies of the tables */
     const uint8_t *d_xlut;
     const uint8_t *d_ylut;
+    const uint8_t *d_mask;         /* optional [Yres*Xres] pixel -> symbol table installed by ScanMatch.maskFromArray */
+                                   /* (scanmatch.py:199-200); NULL = the regular grid (ylut[y]*Xbin + xlut[x])         */
 } spb_score_cfg;
 
 /* ------------------------------------------------------------------------
@@ -139,10 +141,45 @@ int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const 
  *   scores are NaN are dropped too.
  *   d_out [n_groups, 11] f32: slots 5..10 = SM w/o duration, SM with duration,
  *   SED mean, STDE mean, SED best (min), STDE best (max); means divide by
- *   group_size; slots 0..4 (MultiMatch, out of scope) NaN; all NaN if no row survives.
+ *   group_size; slots 0..4 (MultiMatch, out of scope) hold the placeholder 0; the whole row is NaN
+ *   if no row survives (what the reference returns, and what train.py:237 rejects a trial on).
  *   d_reward [n_groups] f64 or NULL: harmonic mean of slots 5, 6 (train.py:252).  */
 int spb_reduce_pairs_eval(const double *d_scores, const uint8_t *d_valid, int64_t n_groups, int32_t group_size,
                           float *d_out, double *d_reward, spb_stream stream);
+
+/* The same reduction with everything the drivers need in ONE pass over the table
+ * (pairs_eval :284-340, evaluation's aggregation :211-237, the SCST trial-rejection rule train.py:237-238):
+ *   - images with fewer subjects than group_size (lists padded by the packer): d_group_count[g % n_images]
+ *     real subjects; padded pairs are skipped and the table divides by the real count (len(gt), :329);
+ *   - the MultiMatch NaN rule computed here from the path lengths (min_len_valid = 3; 0 = off) instead of a
+ *     caller-built mask: needs the pair maps of spb_score_pairs and both packs' d_len;
+ *   - d_acc: running sums over ALL real pairs (evaluation() eliminates nothing), added to on every call:
+ *     [0..3] sum of (SM-wd, SM-wod, SED, STDE), [4..7] sums of squares, [8..9] sum of the per-group SED min /
+ *     STDE max, [10..11] their squares, [12] pairs, [13] groups, [14] groups with a surviving row.  The buffer
+ *     holds spb_reduce_acc_bytes() bytes (result slots + per-block partials + a counter), zero-initialised
+ *     once by the caller; the sum order is fixed (no floating-point atomics), so results are reproducible;
+ *   - d_group_valid [n_groups] u8: 1 where at least one row survives (a trial is accepted iff all are 1).
+ * Slots 0..4 of d_out are 0 where a row survives (MultiMatch placeholder) and the whole row is NaN otherwise. */
+typedef struct spb_reduce_args {
+    const double *d_scores;        /* [n_groups * group_size, 4] */
+    const uint8_t *d_valid;        /* optional caller mask [n_groups * group_size] */
+    const int32_t *d_pair_h;       /* optional, with d_pair_s / d_len_h / d_len_s and min_len_valid > 0 */
+    const int32_t *d_pair_s;
+    const int32_t *d_len_h;
+    const int32_t *d_len_s;
+    const int32_t *d_group_count;  /* optional [n_images] */
+    float *d_out;                  /* optional [n_groups, 11] */
+    double *d_reward;              /* optional [n_groups] */
+    uint8_t *d_group_valid;        /* optional [n_groups] */
+    double *d_acc;                 /* optional, spb_reduce_acc_bytes() bytes */
+    int64_t acc_bytes;
+    int64_t n_groups;
+    int32_t group_size, n_images, min_len_valid;
+    int32_t acc_blocks;            /* set by the library */
+} spb_reduce_args;
+
+int64_t spb_reduce_acc_bytes(void);
+int spb_reduce_pairs(const spb_reduce_args *args, spb_stream stream);
 
 /* ------------------------------------------------------------------------
  * K5 sample_paths.  Replaces Sampling.random_sample + generate_scanpath
@@ -174,6 +211,75 @@ int spb_sample_paths(const float *d_probs, const float *d_mu, const float *d_sig
 int spb_generate_scanpaths(const int32_t *d_actions, const float *d_dur, int64_t n_samples, int32_t T,
                            const spb_sample_geom *geom, float *d_action_mask, float *d_duration_mask,
                            float *d_length, double *d_xyd, int32_t *d_len, spb_stream stream);
+
+/* ------------------------------------------------------------------------
+ * a14 log-likelihoods (models/loss.py:10-45) and f4, the self-critical (SCST) loss tail
+ * (OSIE/train.py:242-258; COCO_Search18/train.py:255-287; AiR/train.py:281-342), forward and
+ * analytic backward.  eps = 1e-7; log-normal density with sigma2 as the VARIANCE;
+ * LogAction / LogDuration rows are divided by the whole batch's mask.sum() (quirks kept).
+ * ---------------------------------------------------------------------- */
+
+/* LogAction (loss.py:34-37) and LogDuration (:39-45) for K stacked calls ("trials") over the same N images:
+ *   d_log_actions[k,n]   = sum_t log(p[k,n,t] + eps) action_mask[k,n,t] / sum(action_mask[k])
+ *   d_log_durations[k,n] = sum_t logpdf(x[k,n,t]; mu[n,t], sigma2[n,t]) duration_mask[k,n,t] / sum(duration_mask[k])
+ * p is d_p [K,N,T] or, when d_p is NULL, gathered from d_probs [N,T,A] at d_actions [K,N,T] (sampling.py:24).
+ * Either output may be NULL.  d_mask_sums [K,2] (or NULL) receives the two mask sums per trial. */
+int spb_loglik_rows(const float *d_p, const float *d_probs, const int32_t *d_actions, const float *d_x,
+                    const float *d_mu, const float *d_sigma2, const float *d_action_mask,
+                    const float *d_duration_mask, int32_t K, int32_t N, int32_t T, int32_t A,
+                    float *d_log_actions, float *d_log_durations, float *d_mask_sums, spb_stream stream);
+/* Backward for upstream row gradients [K,N]: d_grad_p [K,N,T]; d_grad_mu / d_grad_sigma2 [N,T] (summed over
+ * the trials in order); d_grad_x [K,N,T].  Outputs may be NULL. */
+int spb_loglik_rows_backward(const float *d_p, const float *d_x, const float *d_mu, const float *d_sigma2,
+                             const float *d_action_mask, const float *d_duration_mask, const float *d_mask_sums,
+                             const float *d_grad_log_actions, const float *d_grad_log_durations, int32_t K, int32_t N,
+                             int32_t T, float *d_grad_p, float *d_grad_mu, float *d_grad_sigma2, float *d_grad_x,
+                             spb_stream stream);
+
+/* CrossEntropyLoss (loss.py:10-14): logits [rows, A], dense target gt [rows, A], mask [rows].
+ * Forward (d_grad_logits NULL): d_row_loss [rows] scratch, d_loss [1], d_mask_sum [1] written.
+ * Backward (d_grad_logits given): d_grad_out [1] upstream gradient, d_mask_sum from the forward call. */
+int spb_cross_entropy(const float *d_logits, const float *d_gt, const float *d_mask, int64_t rows, int32_t A,
+                      float *d_row_loss, float *d_loss, float *d_mask_sum, const float *d_grad_out,
+                      float *d_grad_logits, spb_stream stream);
+
+/* MLPLogNormalDistribution (loss.py:27-32): -sum_{mask == 1} logpdf(gt; mu, sigma2) / mask.sum(), n elements.
+ * Forward (d_grad_mu NULL): d_item [n] scratch, d_loss [1], d_mask_sum [1]; backward: d_grad_mu, d_grad_sigma2 [n]. */
+int spb_lognormal_nll(const float *d_mu, const float *d_sigma2, const float *d_gt, const float *d_mask, int64_t n,
+                      float *d_item, float *d_loss, float *d_mask_sum, const float *d_grad_out, float *d_grad_mu,
+                      float *d_grad_sigma2, spb_stream stream);
+
+/* The SCST tail in two launches.  Inputs: the decoder outputs of N images, K sampled trials
+ * (spb_sample_paths) and their rewards (spb_reduce_pairs: harmonic mean of ScanMatch w/o and with duration).
+ *   accepted trial : all of its N images kept a scored pair (d_group_valid, train.py:237-238) and no reward is NaN;
+ *                    the first k_use accepted trials are used (d_trial_used[k] = 1; d_trial_used[K] = how many --
+ *                    fewer than k_use means the caller has to sample more, the reference loops until it has them)
+ *   d_adv[k,n]     = reward[k,n] - mean over used trials of reward[.,n]  (+ d_extra_adv[k,n] if given: the hook
+ *                    for AiR's consistency-divergence term, AiR/train.py:322-333)
+ *   d_loss[0..2]   = loss, loss_actions, loss_duration = sum (-LogAction - LogDuration) * adv    (train.py:256-258)
+ * spb_scst_loss_backward writes d loss / d all_actions_prob [N,T,A] (zero-filled, then the gather's scatter),
+ * d loss / d log_normal_mu and / d log_normal_sigma2 [N,T] for the upstream gradient d_grad_loss [3] on
+ * (loss, loss_actions, loss_duration) (NULL = back-propagate `loss` with gradient 1). */
+typedef struct spb_scst_args {
+    const float *d_probs;          /* [N,T,A] all_actions_prob */
+    const float *d_mu, *d_sigma2;  /* [N,T] */
+    const int32_t *d_actions;      /* [K,N,T] */
+    const float *d_dur;            /* [K,N,T] sampled durations (constants: train.py:233 clones .data) */
+    const float *d_action_mask, *d_duration_mask; /* [K,N,T] */
+    const double *d_reward;        /* [K,N] */
+    const uint8_t *d_group_valid;  /* [K,N] or NULL */
+    const float *d_extra_adv;      /* [K,N] or NULL */
+    float *d_loss;                 /* [3] */
+    float *d_adv;                  /* [K,N] */
+    float *d_log_actions, *d_log_durations; /* [K,N] */
+    float *d_mask_sums;            /* [K,2] */
+    int32_t *d_trial_used;         /* [K+1] */
+    int32_t N, T, A, K, k_use, reserved;
+} spb_scst_args;
+
+int spb_scst_loss(const spb_scst_args *args, spb_stream stream);
+int spb_scst_loss_backward(const spb_scst_args *args, const float *d_grad_loss, float *d_grad_probs,
+                           float *d_grad_mu, float *d_grad_sigma2, spb_stream stream);
 
 /* ------------------------------------------------------------------------
  * K6/K7 decode: the 16-step ConvLSTM rollout + prediction head for a wave of

@@ -27,7 +27,14 @@ class ScoreCfg(C.Structure):
     _fields_ = [("sm", ScanMatchCfg),
                 ("sed_height", C.c_int32), ("sed_width", C.c_int32), ("sed_n", C.c_int32), ("reserved", C.c_int32),
                 ("stde_max_dim", C.c_double), ("dur_scale", C.c_double), ("max_sub", C.c_double),
-                ("d_sub_delta", C.c_void_p), ("d_xlut", C.c_void_p), ("d_ylut", C.c_void_p)]
+                ("d_sub_delta", C.c_void_p), ("d_xlut", C.c_void_p), ("d_ylut", C.c_void_p), ("d_mask", C.c_void_p)]
+
+
+class ReduceArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_scores", "d_valid", "d_pair_h", "d_pair_s", "d_len_h", "d_len_s",
+                                          "d_group_count", "d_out", "d_reward", "d_group_valid", "d_acc")] + \
+               [("acc_bytes", C.c_int64), ("n_groups", C.c_int64), ("group_size", C.c_int32), ("n_images", C.c_int32),
+                ("min_len_valid", C.c_int32), ("acc_blocks", C.c_int32)]
 
 
 class PathPack(C.Structure):
@@ -55,6 +62,8 @@ SYMBOLS = {
     "spb_score_pairs": (C.c_int, [C.POINTER(PathPack), C.POINTER(PathPack), P, P, I64, C.POINTER(ScoreCfg), P, P,
                                   I64, P, P]),
     "spb_reduce_pairs_eval": (C.c_int, [P, P, I64, I32, P, P, P]),
+    "spb_reduce_acc_bytes": (I64, []),
+    "spb_reduce_pairs": (C.c_int, [C.POINTER(ReduceArgs), P]),
     "spb_sample_paths": (C.c_int, [P, P, P, P, P, U64, I32, I32, I32, I32, C.POINTER(SampleGeom), P, P, P, P, P, P,
                                    P, P, P]),
     "spb_generate_scanpaths": (C.c_int, [P, P, I64, I32, C.POINTER(SampleGeom), P, P, P, P, P, P]),
@@ -86,6 +95,22 @@ SYMBOLS.update({
     "spb_wino_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "spb_split_fp16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_float, C.c_void_p]),
+})
+
+class ScstArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_probs", "d_mu", "d_sigma2", "d_actions", "d_dur", "d_action_mask",
+                                          "d_duration_mask", "d_reward", "d_group_valid", "d_extra_adv", "d_loss",
+                                          "d_adv", "d_log_actions", "d_log_durations", "d_mask_sums", "d_trial_used")] + \
+               [(n, C.c_int32) for n in ("N", "T", "A", "K", "k_use", "reserved")]
+
+
+SYMBOLS.update({
+    "spb_loglik_rows": (C.c_int, [P] * 8 + [I32] * 4 + [P] * 4),
+    "spb_loglik_rows_backward": (C.c_int, [P] * 9 + [I32] * 3 + [P] * 5),
+    "spb_cross_entropy": (C.c_int, [P, P, P, I64, I32, P, P, P, P, P, P]),
+    "spb_lognormal_nll": (C.c_int, [P, P, P, P, I64, P, P, P, P, P, P, P]),
+    "spb_scst_loss": (C.c_int, [C.POINTER(ScstArgs), P]),
+    "spb_scst_loss_backward": (C.c_int, [C.POINTER(ScstArgs), P, P, P, P, P]),
 })
 
 _lib = None

@@ -43,7 +43,7 @@ void prof_end(cudaStream_t s);
         }                                                                                    \
     } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+int num_sms();   // SM count of the current device (148 on B200), queried once per device
 
 __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
     return __shfl_up_sync(0xffffffffu, v, delta);

@@ -685,7 +685,7 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
         return SPB_ERR_ARG;
     }
     const int num_tiles = (int)tiles64;
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;       // persistent: one CTA per SM
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();       // persistent: one CTA per SM
 #define SPB_LAUNCH_TC(KS_)                                                                                          \
     SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
     conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
@@ -738,7 +738,7 @@ int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, con
         return SPB_ERR_CUDA;
     }
     const int num_tiles = (int)(wg::kPosJ * nct * ntb);
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
     wino_gemm_tc_kernel<<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb, cols,
                                                               rows_pad, inv_scale);

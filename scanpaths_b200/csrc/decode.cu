@@ -1015,7 +1015,7 @@ extern "C" int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t 
     } else {
         const int64_t total = n_outer * C * HW;
         int64_t blocks = (total + 255) / 256;
-        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+        if (blocks > num_sms() * 16) blocks = num_sms() * 16;
         split_plain_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_x, (__half *)d_hi, (__half *)d_lo, total, scale);
     }
     SPB_LAUNCH_CHECK();

@@ -39,7 +39,8 @@ prep_paths_kernel(const double *__restrict__ xyd, const int32_t *__restrict__ le
         y = y >= cfg.sm.Yres ? (double)(cfg.sm.Yres - 1) : y;
         const int xi = (int)x, yi = (int)y;                               // int(): toward zero
         const long long ti = (long long)t;
-        sym[idx] = (uint8_t)(cfg.d_ylut[yi] * cfg.sm.Xbin + cfg.d_xlut[xi]);
+        sym[idx] = cfg.d_mask ? cfg.d_mask[(int64_t)yi * cfg.sm.Xres + xi]       // maskFromArray (scanmatch.py:199)
+                              : (uint8_t)(cfg.d_ylut[yi] * cfg.sm.Xbin + cfg.d_xlut[xi]);
         int r = 1;
         if (cfg.sm.TempBin != 0.0) {
             double q = rint((double)ti / cfg.sm.TempBin);                 // numpy.round: half to even
@@ -85,7 +86,7 @@ extern "C" int spb_prep_paths(const double *d_xyd, const int32_t *d_len, int64_t
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t total = n_paths * (int64_t)lmax;
     int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)spb::kNumSMs * 16;
+    const int64_t cap = (int64_t)spb::num_sms() * 16;
     if (blocks > cap) blocks = cap;
     spb::prep_paths_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_xyd, d_len, n_paths, lmax, *cfg, d_sym, d_run, d_sed,
                                                              d_xyn);

@@ -177,7 +177,7 @@ extern "C" int spb_sample_paths(const float *d_probs, const float *d_mu, const f
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t rows = (int64_t)N * T;
     int64_t blocks = (rows + 7) / 8;
-    const int64_t cap = (int64_t)spb::kNumSMs * 8;
+    const int64_t cap = (int64_t)spb::num_sms() * 8;
     if (blocks > cap) blocks = cap;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     spb::prof_begin(spb::kTagSample, s);
@@ -203,7 +203,7 @@ extern "C" int spb_generate_scanpaths(const int32_t *d_actions, const float *d_d
     SPB_CHECK_ARG(d_actions && d_dur && d_action_mask && d_duration_mask && d_length && d_xyd && d_len,
                   "null device pointer");
     int64_t fb = (n_samples + 255) / 256;
-    const int64_t cap = (int64_t)spb::kNumSMs * 8;
+    const int64_t cap = (int64_t)spb::num_sms() * 8;
     if (fb > cap) fb = cap;
     spb::finalize_paths_kernel<<<(unsigned)fb, 256, 0, (cudaStream_t)stream>>>(
         d_actions, d_dur, n_samples, T, *geom, d_action_mask, d_duration_mask, d_length, d_xyd, d_len);

@@ -18,6 +18,7 @@
 // Not HBM-bound (about 0.45 KB per 15 pairs): the limiter is
 // instruction issue, so the roofline unit is DP cell-updates/s.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -282,14 +283,23 @@ score_pairs_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restrict__
     uint8_t *ar = base + L.ar, *ac = base + L.ac, *br = base + L.br, *bc = base + L.bc;
     uint8_t *awr = base + L.awr, *awc = base + L.awc, *bwr = base + L.bwr, *bwc = base + L.bwc;
 
-    const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int wpb = blockDim.x >> 5;                  // 8 unless long scanpaths need more shared memory per warp
+    const int64_t gwarp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
     double *bnd = workspace ? workspace + gwarp * ws_per_warp : nullptr;
     const int xbin = cfg.sm.Xbin;
     const double gap = cfg.sm.GapValue;
 
     for (int64_t p = gwarp; p < n_pairs; p += nwarps) {
         const int64_t ia = pair_h[p], ib = pair_s[p];
+        if (ia < 0 || ia >= A.n_paths || ib < 0 || ib >= B.n_paths) {      // stale / foreign pair map: fail loudly
+            if (lane == 0) {
+                atomicExch(err, 2);
+                double *o = scores + 4 * p;
+                o[0] = o[1] = o[2] = o[3] = nan("");
+            }
+            continue;
+        }
         const int La = A.d_len[ia], Lb = B.d_len[ib];
         const int n_wd = A.d_nwd[ia], m_wd = B.d_nwd[ib];
         int na_runs = 0, nb_runs = 0;
@@ -353,39 +363,108 @@ score_pairs_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restrict__
 }
 
 // ---------------------------------------------------------------------------
-// a7: per-group reduction of the score table (pairs_eval aggregation).
+// a7: per-group reduction of the score table (pairs_eval aggregation, OSIE/utils/evaluation.py:325-338) and the
+// global sums behind `evaluation`'s mean / std / best (:211-237), in one pass over the table.
+//   group g = one simulated path against the (padded) subject list of image g % n_images;
+//   real pair      : s < count[image]                       (subjects padded in by pack_subject_lists are skipped)
+//   surviving row  : real, both paths >= min_len_valid fixations (the MultiMatch NaN rule), no NaN score
+//   table row      : sums of the surviving rows / count[image]  (the reference divides by len(gt), :329)
+//   accumulators   : over ALL real pairs (evaluation() does not eliminate rows): sum, sum of squares of the four
+//                    scores, of the per-group SED min / STDE max, pair and group counts.  Deterministic: per-block
+//                    partials, summed in block order by the last block to finish (no floating-point atomics).
 // ---------------------------------------------------------------------------
+constexpr int kAccSlots = 16;     // 0-3 sum, 4-7 sumsq, 8-9 best sums, 10-11 best sumsq, 12 real pairs, 13 groups, 14 surviving groups
+
 __global__ void __launch_bounds__(256)
-reduce_pairs_eval_kernel(const double *__restrict__ scores, const uint8_t *__restrict__ valid, int64_t n_groups,
-                         int group_size, float *__restrict__ out, double *__restrict__ reward) {
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups;
+reduce_pairs_kernel(spb_reduce_args a) {
+    __shared__ double sh[8][kAccSlots];
+    __shared__ bool last;
+    double loc[kAccSlots];
+#pragma unroll
+    for (int i = 0; i < kAccSlots; ++i) loc[i] = 0.0;
+    const int gs = a.group_size;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < a.n_groups;
          g += (int64_t)gridDim.x * blockDim.x) {
+        const int img = a.n_images > 0 ? (int)(g % a.n_images) : 0;
+        const int cnt = a.d_group_count ? min(max(a.d_group_count[img], 0), gs) : gs;
         double s_wod = 0, s_wd = 0, s_sed = 0, s_stde = 0, best_sed = INFINITY, best_stde = -INFINITY;
+        double all_best_sed = INFINITY, all_best_stde = -INFINITY;
         int kept = 0;
-        for (int s = 0; s < group_size; ++s) {
-            const double *r = scores + 4 * (g * group_size + s);
-            const bool ok = (valid == nullptr || valid[g * group_size + s]) &&
-                            !(isnan(r[0]) || isnan(r[1]) || isnan(r[2]) || isnan(r[3]));
+        for (int s = 0; s < cnt; ++s) {
+            const int64_t p = g * gs + s;
+            const double *r = a.d_scores + 4 * p;
+            const double r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+            loc[0] += r0; loc[1] += r1; loc[2] += r2; loc[3] += r3;
+            loc[4] += r0 * r0; loc[5] += r1 * r1; loc[6] += r2 * r2; loc[7] += r3 * r3;
+            loc[12] += 1.0;
+            all_best_sed = fmin(all_best_sed, r2); all_best_stde = fmax(all_best_stde, r3);
+            bool ok = (a.d_valid == nullptr || a.d_valid[p]) && !(isnan(r0) || isnan(r1) || isnan(r2) || isnan(r3));
+            if (ok && a.min_len_valid > 0 && a.d_pair_h != nullptr)
+                ok = a.d_len_h[a.d_pair_h[p]] >= a.min_len_valid && a.d_len_s[a.d_pair_s[p]] >= a.min_len_valid;
             if (!ok) continue;
             ++kept;
-            s_wd += r[0]; s_wod += r[1]; s_sed += r[2]; s_stde += r[3];
-            best_sed = fmin(best_sed, r[2]); best_stde = fmax(best_stde, r[3]);
+            s_wd += r0; s_wod += r1; s_sed += r2; s_stde += r3;
+            best_sed = fmin(best_sed, r2); best_stde = fmax(best_stde, r3);
         }
-        float *o = out + 11 * g;
+        if (cnt > 0) {
+            loc[8] += all_best_sed; loc[9] += all_best_stde;
+            loc[10] += all_best_sed * all_best_sed; loc[11] += all_best_stde * all_best_stde;
+            loc[13] += 1.0;
+        }
         const float qnan = __int_as_float(0x7fc00000);
-        for (int i = 0; i < 11; ++i) o[i] = qnan;
         double rw = nan("");
-        if (kept > 0) {
-            const double inv = 1.0 / (double)group_size;      // divides by len(gt), evaluation.py:329
-            o[5] = (float)(s_wod / group_size); o[6] = (float)(s_wd / group_size);
-            o[7] = (float)(s_sed / group_size); o[8] = (float)(s_stde / group_size);
-            o[9] = (float)best_sed; o[10] = (float)best_stde;
-            (void)inv;
-            const double a = (double)o[5], b = (double)o[6];   // reward is computed from the float32 table (train.py:241,252)
-            rw = (a > 0.0 && b > 0.0) ? 2.0 / (1.0 / a + 1.0 / b) : 0.0;
+        if (a.d_out) {
+            float *o = a.d_out + 11 * g;
+            if (kept > 0) {
+                // slots 0..4 are MultiMatch's (external package, out of scope): a finite placeholder, so that the
+                // reference's `np.any(np.isnan(metrics_reward))` trial rejection (train.py:237) sees NaN exactly
+                // where the reference does -- when no row of the image survives
+                o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
+                o[5] = (float)(s_wod / cnt); o[6] = (float)(s_wd / cnt);
+                o[7] = (float)(s_sed / cnt); o[8] = (float)(s_stde / cnt);
+                o[9] = (float)best_sed; o[10] = (float)best_stde;
+            } else {
+                for (int i = 0; i < 11; ++i) o[i] = qnan;
+            }
         }
-        if (reward) reward[g] = rw;
+        if (kept > 0) {
+            // the reward is computed from the float32 table (train.py:241,252: scipy.stats.hmean of slots 5, 6)
+            const double x = (double)(float)(s_wod / cnt), y = (double)(float)(s_wd / cnt);
+            rw = (x > 0.0 && y > 0.0) ? 2.0 / (1.0 / x + 1.0 / y) : 0.0;
+            loc[14] += 1.0;
+        }
+        if (a.d_reward) a.d_reward[g] = rw;
+        if (a.d_group_valid) a.d_group_valid[g] = kept > 0 ? 1 : 0;
     }
+    if (a.d_acc == nullptr) return;
+    // block partials in a fixed order: lanes -> warps -> blocks
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kAccSlots; ++i) {
+        double v = loc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[w][i] = v;
+    }
+    __syncthreads();
+    double *part = a.d_acc + kAccSlots;                 // [gridDim.x][kAccSlots], then the arrival counter
+    unsigned int *counter = reinterpret_cast<unsigned int *>(a.d_acc + kAccSlots + (int64_t)a.acc_blocks * kAccSlots);
+    if (threadIdx.x < kAccSlots) {
+        double v = 0.0;
+        for (int i = 0; i < 8; ++i) v += sh[i][threadIdx.x];
+        part[(int64_t)blockIdx.x * kAccSlots + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < kAccSlots) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += part[(int64_t)b * kAccSlots + threadIdx.x];
+        a.d_acc[threadIdx.x] += v;
+    }
+    if (threadIdx.x == 0) *counter = 0;                 // ready for the next launch
 }
 
 }  // namespace spb
@@ -393,7 +472,7 @@ reduce_pairs_eval_kernel(const double *__restrict__ scores, const uint8_t *__res
 extern "C" int64_t spb_score_workspace_bytes(int64_t max_human_nwd) {
     if (max_human_nwd < 0) max_human_nwd = 0;
     const int64_t per_warp = (max_human_nwd + 2 + 1) & ~(int64_t)1;
-    return per_warp * 8 * spb::kWarpsPerBlock * spb::kNumSMs * 4;
+    return per_warp * 8 * 32 * spb::num_sms();               // <= 32 resident warps per SM run this kernel
 }
 
 extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const int32_t *d_pair_h,
@@ -411,32 +490,64 @@ extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *
     }
     const spb::PairLayout L = spb::make_layout(human->lmax, sim->lmax);
     const int ntab_bytes = (cfg->sm.Xbin * cfg->sm.Ybin * 8 + 15) & ~15;
-    const size_t smem = (size_t)ntab_bytes + (size_t)L.bytes * spb::kWarpsPerBlock;
+    // 8 warps per block unless the per-warp slice (the STDE tiles grow with lmax_h x lmax_s) needs more room:
+    // long human scanpaths (the AiR / COCO evaluation sets do not truncate them) run with 4, 2 or 1 warps
+    int wpb = spb::kWarpsPerBlock;
+    while (wpb > 1 && (size_t)ntab_bytes + (size_t)L.bytes * wpb > 227 * 1024) wpb >>= 1;
+    const size_t smem = (size_t)ntab_bytes + (size_t)L.bytes * wpb;
     if (smem > 227 * 1024) {
-        spb::set_error("spb_score_pairs: lmax %d x %d needs %zu B of shared memory per block (> 227 KB)", human->lmax,
+        spb::set_error("spb_score_pairs: lmax %d x %d needs %zu B of shared memory per warp (> 227 KB)", human->lmax,
                        sim->lmax, smem);
         return SPB_ERR_UNSUPPORTED;
     }
     SPB_CUDA(cudaFuncSetAttribute(spb::score_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spb::score_pairs_kernel,
-                                                           spb::kWarpsPerBlock * 32, smem));
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spb::score_pairs_kernel, wpb * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int64_t blocks = (int64_t)spb::kNumSMs * per_sm;            // persistent grid, whole waves
-    const int64_t need = (n_pairs + spb::kWarpsPerBlock - 1) / spb::kWarpsPerBlock;
+    if (per_sm * wpb > 32) per_sm = 32 / wpb;
+    int64_t blocks = (int64_t)spb::num_sms() * per_sm;          // persistent grid, whole waves
+    const int64_t need = (n_pairs + wpb - 1) / wpb;
     if (blocks > need) blocks = need;
     int64_t ws_per_warp = 0;
     if (d_workspace != nullptr && workspace_bytes > 0) {
-        ws_per_warp = workspace_bytes / 8 / (blocks * spb::kWarpsPerBlock);
+        ws_per_warp = workspace_bytes / 8 / (blocks * wpb);
         ws_per_warp &= ~(int64_t)1;
     }
     spb::prof_begin(spb::kTagScore, (cudaStream_t)stream);
-    spb::score_pairs_kernel<<<(unsigned)blocks, spb::kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+    spb::score_pairs_kernel<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
         *human, *sim, d_pair_h, d_pair_s, n_pairs, *cfg, d_scores, ws_per_warp > 0 ? (double *)d_workspace : nullptr,
         ws_per_warp, d_err);
     SPB_LAUNCH_CHECK();
     spb::prof_end((cudaStream_t)stream);
+    return SPB_OK;
+}
+
+static int reduce_blocks(int64_t n_groups) {
+    int64_t blocks = (n_groups + 255) / 256;
+    const int64_t cap = (int64_t)spb::num_sms() * 4;
+    return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+extern "C" int64_t spb_reduce_acc_bytes(void) {
+    // 16 result slots + per-block partials of the largest grid + the arrival counter
+    return (int64_t)(spb::kAccSlots + (int64_t)spb::num_sms() * 4 * spb::kAccSlots + 2) * 8;
+}
+
+extern "C" int spb_reduce_pairs(const spb_reduce_args *args, spb_stream stream) {
+    SPB_CHECK_ARG(args != nullptr, "null struct pointer");
+    SPB_CHECK_ARG(args->n_groups >= 0 && args->group_size > 0, "bad sizes");
+    if (args->n_groups == 0) return SPB_OK;
+    SPB_CHECK_ARG(args->d_scores != nullptr, "null device pointer");
+    SPB_CHECK_ARG(args->d_group_count == nullptr || args->n_images > 0, "group counts need n_images");
+    SPB_CHECK_ARG(args->min_len_valid <= 0 || args->d_pair_h == nullptr ||
+                      (args->d_pair_s && args->d_len_h && args->d_len_s),
+                  "the length rule needs pair maps and both length arrays");
+    spb_reduce_args a = *args;
+    const int blocks = reduce_blocks(a.n_groups);
+    a.acc_blocks = (int32_t)((int64_t)spb::num_sms() * 4);
+    if (a.d_acc) SPB_CHECK_ARG(a.acc_bytes >= spb_reduce_acc_bytes(), "accumulator buffer smaller than spb_reduce_acc_bytes()");
+    spb::reduce_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    SPB_LAUNCH_CHECK();
     return SPB_OK;
 }
 
@@ -445,10 +556,9 @@ extern "C" int spb_reduce_pairs_eval(const double *d_scores, const uint8_t *d_va
     SPB_CHECK_ARG(n_groups >= 0 && group_size > 0, "bad sizes");
     if (n_groups == 0) return SPB_OK;
     SPB_CHECK_ARG(d_scores && d_out, "null device pointer");
-    int64_t blocks = (n_groups + 255) / 256;
-    if (blocks > spb::kNumSMs * 8) blocks = spb::kNumSMs * 8;
-    spb::reduce_pairs_eval_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_scores, d_valid, n_groups,
-                                                                                       group_size, d_out, d_reward);
-    SPB_LAUNCH_CHECK();
-    return SPB_OK;
+    spb_reduce_args a;
+    memset(&a, 0, sizeof(a));
+    a.d_scores = d_scores; a.d_valid = d_valid; a.n_groups = n_groups; a.group_size = group_size;
+    a.d_out = d_out; a.d_reward = d_reward;
+    return spb_reduce_pairs(&a, stream);
 }

@@ -353,7 +353,12 @@ class baseline(nn.Module):
             raise NotImplementedError("training_process stays in PyTorch (out of scope); call under eval()")
         return _result_dict(self.task, *self.decoder().decode(visual_feature, attention_maps, tasks))
 
-    def forward(self, images, attention_maps=None, tasks=None):
+    def forward(self, images, attention_maps=None, tasks=None, performances=None):
+        """OSIE: forward(images); COCO-Search18: forward(images, attention_maps, tasks); AiR:
+        forward(images, attention_maps, performances=None) -- the third positional of the AiR reference is
+        `performances` (AiR/models/baseline_attention.py:253), which only its training branch reads."""
+        if self.task == "AiR":
+            tasks = None                                   # a positional `performances` lands here: inference ignores it
         if self.training:
             raise NotImplementedError("training_process (with gradients) is out of scope of the CUDA path")
         if images.shape[1] == E:                       # already visual_feature [N,512,30,40]

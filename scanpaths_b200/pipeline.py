@@ -4,7 +4,7 @@ the SCST reward loop (train.py:216-254) do per batch, in waves of images that st
 the device from the feature map to the reduced score table.
 
 Host side only: every stage is one C-ABI call (spb_decode, spb_sample_paths,
-spb_prep_paths, spb_score_pairs, spb_reduce_pairs_eval).
+spb_prep_paths, spb_score_pairs, spb_reduce_pairs); no ATen arithmetic runs between them.
 """
 from __future__ import annotations
 
@@ -14,6 +14,8 @@ import torch
 from . import scoring as S
 from .models.baseline_attention import CudaDecoder
 from .models.sampling import Sampling
+
+MIN_LEN_VALID = 3    # multimatch_gaze's NaN rule, which pairs_eval's row elimination follows
 
 
 class ScanpathPipeline:
@@ -26,28 +28,37 @@ class ScanpathPipeline:
         self.cfg = S.ScoreConfig.evaluation(device=self.device, dur_scale=1000.0)
         self.humans = None
         self.n_subjects = 0
+        self.subject_count = None
         self._pairs = {}
         self._ws = None
+        self._cs = None
 
     # ---- human scanpaths: packed once, resident on the device
-    def set_humans(self, xyd, lens):
-        """xyd [N, S, Lmax, 3] f64 (x, y, seconds), lens [N, S] i32 (numpy or torch, host or device)."""
+    def set_humans(self, xyd, lens, n_subjects=None):
+        """xyd [N, S, Lmax, 3] f64 (x, y, seconds), lens [N, S] i32, n_subjects [N] i32 or None (numpy or torch,
+        host or device).  `n_subjects` is the real subject count per image when the lists were padded to a common
+        S (scoring.pack_subject_lists): padded subjects are never scored into any result."""
         xyd = torch.as_tensor(xyd, dtype=torch.float64)
         lens = torch.as_tensor(lens, dtype=torch.int32)
         N, Sn, L, _ = xyd.shape
         self.n_subjects = Sn
+        self._pairs.clear()                     # pair maps depend on the subject count of THIS set of humans
         self.humans = S.prep_paths(xyd.reshape(N * Sn, L, 3).to(self.device, non_blocking=True),
                                    lens.reshape(N * Sn).to(self.device, non_blocking=True), self.cfg)
+        self.subject_count = None
+        if n_subjects is not None:
+            self.subject_count = torch.as_tensor(n_subjects, dtype=torch.int32).to(self.device, non_blocking=True)
+            assert self.subject_count.numel() == N
         self._ws = S.Workspace(int(self.humans.nwd.max().item()), self.device)
         return self.humans
 
     def _copy_stream(self):
-        if getattr(self, "_cs", None) is None:
+        if self._cs is None:
             self._cs = torch.cuda.Stream(device=self.device)
         return self._cs
 
     def _pair_map(self, n, n0):
-        key = (n, n0)
+        key = (n, n0, self.n_subjects, self.K)
         if key not in self._pairs:
             ph, ps = S.grid_pairs(n, self.K, self.n_subjects, self.device)
             self._pairs[key] = ((ph + n0 * self.n_subjects).contiguous(), ps)
@@ -55,24 +66,32 @@ class ScanpathPipeline:
                 self._pairs.pop(next(iter(self._pairs)))
         return self._pairs[key]
 
-    def run(self, visual_feature, attention_maps=None, tasks=None, keep_scores=False, valid_min_len=0,
-            keep_paths=False):
+    def run(self, visual_feature, attention_maps=None, tasks=None, keep_scores=False, valid_min_len=MIN_LEN_VALID,
+            keep_paths=False, paths_host=None):
         """visual_feature [N,512,30,40] f32 on the device or in (pinned) host memory.
-        Returns dict: table [HD, K, N, 11] f32 (pairs_eval layout per sample), reward [HD, K, N] f64,
-        metrics (the `evaluation` aggregate over all pairs) and optionally the raw scores."""
+        Returns dict: table [HD, K, N, 11] f32 (pairs_eval layout per sample; rows follow the reference's
+        elimination rule with `valid_min_len`), reward [HD, K, N] f64, group_valid [HD, K, N] u8 (0 where
+        train.py:237 would reject the trial), acc (the running sums behind `evaluation`'s aggregate over all
+        real pairs) and optionally the raw scores / the sampled scanpaths.
+        paths_host: optional (xyd [HD, K, N, T, 3] f64, len [HD, K, N] i32) pinned host tensors; every wave's
+        sampled scanpaths are copied into them on the side stream (what test.py:135-152 dumps)."""
         assert self.humans is not None, "set_humans() first"
         N = visual_feature.shape[0]
-        dev, K, Sn, HD = self.device, self.K, self.n_subjects, self.decoder.heads
+        assert self.humans.n == N * self.n_subjects, "set_humans() was called for %d images, run() got %d" % (
+            self.humans.n // max(self.n_subjects, 1), N)
+        dev, K, Sn, HD, T = self.device, self.K, self.n_subjects, self.decoder.heads, self.steps
         table = torch.empty((HD, K, N, 11), dtype=torch.float32, device=dev)
         reward = torch.empty((HD, K, N), dtype=torch.float64, device=dev)
+        gvalid = torch.empty((HD, K, N), dtype=torch.uint8, device=dev)
         scores_all = torch.empty((HD, K, N, Sn, 4), dtype=torch.float64, device=dev) if keep_scores else None
-        acc = torch.zeros((HD, 12), dtype=torch.float64, device=dev)   # sum, sumsq (4 each), best sums/sumsq (2+2)
+        accs = [S.new_accumulator(dev) for _ in range(HD)]
         paths = [] if keep_paths else None
         host_in = not visual_feature.is_cuda
         # host input: the next wave's features are copied on a side stream while this wave computes
-        copy_stream = self._copy_stream() if host_in else None
+        copy_stream = self._copy_stream() if (host_in or paths_host is not None) else None
         main = torch.cuda.current_stream(dev)
         starts = list(range(0, N, self.wave))
+        full = len(starts) == 1
 
         def fetch(n0):
             n1 = min(N, n0 + self.wave)
@@ -97,28 +116,42 @@ class ScanpathPipeline:
             tk = None if tasks is None else tasks[n0:n1]
             probs, mu, s2, _ = self.decoder.decode(vf, att, tk)
             ph, ps = self._pair_map(n, n0)
+            cnt = None if self.subject_count is None else self.subject_count[n0:n1]
             for hd in range(HD):
                 smp = self.sampler.sample_paths(probs[hd], mu[hd], s2[hd], K)
                 pp = S.prep_paths(smp["xyd"], smp["len"], self.cfg)
-                sc = S.score_pairs(self.humans, pp, ph, ps, self.cfg, workspace=self._ws, check=False)
-                valid = None
-                if valid_min_len > 0:
-                    valid = ((self.humans.len[ph.long()] >= valid_min_len) &
-                             (pp.len[ps.long()] >= valid_min_len)).to(torch.uint8)
-                tab, rew = S.reduce_pairs_eval(sc, Sn, valid)
-                table[hd, :, n0:n1] = tab.view(K, n, 11)
-                reward[hd, :, n0:n1] = rew.view(K, n)
-                g = sc.view(K * n, Sn, 4)
-                sed_best, stde_best = g[:, :, 2].min(1)[0], g[:, :, 3].max(1)[0]
-                acc[hd, 0:4] += sc.sum(0)
-                acc[hd, 4:8] += (sc * sc).sum(0)
-                acc[hd, 8] += sed_best.sum(); acc[hd, 9] += stde_best.sum()
-                acc[hd, 10] += (sed_best * sed_best).sum(); acc[hd, 11] += (stde_best * stde_best).sum()
-                if keep_scores:
-                    scores_all[hd, :, n0:n1] = sc.view(K, n, Sn, 4)
+                sc = scores_all[hd] if (keep_scores and full) else None
+                sc = S.score_pairs(self.humans, pp, ph, ps, self.cfg, workspace=self._ws, check=False,
+                                   out=None if sc is None else sc.view(-1, 4))
+                # the reduced tables of a wave are dense [K, n, ...] blocks; written in place when one wave
+                # covers the batch, else copied into the [K, N, ...] results
+                tab_w = table[hd].view(K * N, 11) if full else None
+                rew_w = reward[hd].view(K * N) if full else None
+                gv_w = gvalid[hd].view(K * N) if full else None
+                tab_w, rew_w, gv_w = S.reduce_pairs(sc, Sn, n_images=n, group_count=cnt, pair_h=ph, pair_s=ps,
+                                                    len_h=self.humans.len, len_s=pp.len, min_len_valid=valid_min_len,
+                                                    acc=accs[hd], out=tab_w, reward=rew_w, group_valid=gv_w)
+                if not full:
+                    table[hd, :, n0:n1] = tab_w.view(K, n, 11)
+                    reward[hd, :, n0:n1] = rew_w.view(K, n)
+                    gvalid[hd, :, n0:n1] = gv_w.view(K, n)
+                    if keep_scores:
+                        scores_all[hd, :, n0:n1] = sc.view(K, n, Sn, 4)
                 if keep_paths:
                     paths.append((hd, n0, n1, smp))
-        out = {"table": table, "reward": reward, "acc": acc, "n_pairs": K * N * Sn, "n_groups": K * N}
+                if paths_host is not None:
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(done)
+                        paths_host[0][hd, :, n0:n1].copy_(smp["xyd"].view(K, n, T, 3), non_blocking=True)
+                        paths_host[1][hd, :, n0:n1].copy_(smp["len"].view(K, n), non_blocking=True)
+                    smp["xyd"].record_stream(copy_stream)
+                    smp["len"].record_stream(copy_stream)
+        if paths_host is not None:
+            main.wait_stream(copy_stream)
+        acc = torch.stack([a[:16] for a in accs], 0)
+        out = {"table": table, "reward": reward, "group_valid": gvalid, "acc": acc}
         if keep_scores:
             out["scores"] = scores_all
         if keep_paths:
@@ -129,7 +162,7 @@ class ScanpathPipeline:
     def metrics(out, head=0):
         """Host-side view of the accumulators in the shape of `evaluation`'s return (one D2H read)."""
         a = out["acc"][head].cpu().numpy()
-        P, G = out["n_pairs"], out["n_groups"]
+        P, G = max(a[12], 1.0), max(a[13], 1.0)
         mean = a[0:4] / P
         std = np.sqrt(np.maximum(a[4:8] / P - mean ** 2, 0.0))
         bmean = a[8:10] / G

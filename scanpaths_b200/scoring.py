@@ -42,9 +42,21 @@ class ScoreConfig:
         self.d_xlut = torch.from_numpy(self.xlut).to(self.device)
         self.d_ylut = torch.from_numpy(self.ylut).to(self.device)
         h, w = int(stimulus_shape[0]), int(stimulus_shape[1])
+        self.d_mask = None
         self.cfg = _lib.ScoreCfg(self.sm, h, w, int(sed_n), 0, float(max(stimulus_shape)), float(dur_scale),
                                  self.max_sub, self.d_sub_delta.data_ptr(), self.d_xlut.data_ptr(),
-                                 self.d_ylut.data_ptr())
+                                 self.d_ylut.data_ptr(), None)
+
+    def set_mask(self, array):
+        """ScanMatch.maskFromArray (scanmatch.py:199-200): a [Yres, Xres] pixel -> symbol table replaces the
+        regular grid.  Symbols must stay below Xbin*Ybin (they index the substitution table)."""
+        m = np.ascontiguousarray(np.asarray(array))
+        if m.shape != (self.sm.Yres, self.sm.Xres):
+            raise ValueError("mask must be [Yres, Xres] = [%d, %d]" % (self.sm.Yres, self.sm.Xres))
+        if m.min() < 0 or m.max() >= self.sm.Xbin * self.sm.Ybin:
+            raise ValueError("mask symbols must lie in [0, Xbin*Ybin)")
+        self.d_mask = torch.from_numpy(m.astype(np.uint8)).to(self.device)
+        self.cfg.d_mask = self.d_mask.data_ptr()
 
     @classmethod
     def evaluation(cls, device=None, dur_scale=1000.0):
@@ -187,8 +199,12 @@ def score_pairs(human: PathPack, sim: PathPack, pair_h: torch.Tensor, pair_s: to
                                        _lib.ptr(workspace.buf) if workspace else None,
                                        workspace.nbytes if workspace else 0, _lib.ptr(err), _lib.current_stream()),
                    "spb_score_pairs")
-    if check and workspace is not None and int(err.item()) != 0:
-        raise _lib.SpbError("spb_score_pairs: workspace too small for the with-duration strings")
+    if check:
+        e = int(err.item())
+        if e == 2:
+            raise _lib.SpbError("spb_score_pairs: a pair index lies outside its path pack (stale pair map?)")
+        if e != 0:
+            raise _lib.SpbError("spb_score_pairs: workspace too small for the with-duration strings")
     return out
 
 
@@ -205,6 +221,43 @@ def reduce_pairs_eval(scores: torch.Tensor, group_size: int, valid: torch.Tensor
                                              group_size, _lib.ptr(out), _lib.ptr(reward), _lib.current_stream()),
                    "spb_reduce_pairs_eval")
     return out, reward
+
+
+def new_accumulator(device) -> torch.Tensor:
+    """Zeroed f64 buffer for reduce_pairs(acc=...): slots [0:16] are the running sums (see the header)."""
+    n = _lib.load().spb_reduce_acc_bytes() // 8
+    return torch.zeros((n,), dtype=torch.float64, device=device)
+
+
+def reduce_pairs(scores: torch.Tensor, group_size: int, *, n_images: int = 0, group_count: torch.Tensor | None = None,
+                 pair_h: torch.Tensor | None = None, pair_s: torch.Tensor | None = None,
+                 len_h: torch.Tensor | None = None, len_s: torch.Tensor | None = None, min_len_valid: int = 0,
+                 valid: torch.Tensor | None = None, acc: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                 reward: torch.Tensor | None = None, group_valid: torch.Tensor | None = None):
+    """a7 in one pass (spb_reduce_pairs): table [G,11] f32, reward [G] f64, group_valid [G] u8, and the running
+    sums of `evaluation` added into `acc` (new_accumulator).  Padded subjects (index >= group_count[image]) are
+    skipped; with min_len_valid the MultiMatch NaN rule is evaluated on the device from the path lengths."""
+    lib = _lib.load()
+    G = scores.shape[0] // group_size
+    dev = scores.device
+    if out is None:
+        out = torch.empty((G, 11), dtype=torch.float32, device=dev)
+    if reward is None:
+        reward = torch.empty((G,), dtype=torch.float64, device=dev)
+    if group_valid is None:
+        group_valid = torch.empty((G,), dtype=torch.uint8, device=dev)
+    assert out.is_contiguous() and reward.is_contiguous() and group_valid.is_contiguous() and scores.is_contiguous()
+    a = _lib.ReduceArgs()
+    p = lambda t: None if t is None else t.data_ptr()
+    a.d_scores, a.d_valid = scores.data_ptr(), p(valid)
+    a.d_pair_h, a.d_pair_s, a.d_len_h, a.d_len_s = p(pair_h), p(pair_s), p(len_h), p(len_s)
+    a.d_group_count = p(group_count)
+    a.d_out, a.d_reward, a.d_group_valid = out.data_ptr(), reward.data_ptr(), group_valid.data_ptr()
+    a.d_acc, a.acc_bytes = p(acc), (acc.numel() * 8 if acc is not None else 0)
+    a.n_groups, a.group_size, a.n_images, a.min_len_valid = G, int(group_size), int(n_images), int(min_len_valid)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spb_reduce_pairs(C.byref(a), _lib.current_stream()), "spb_reduce_pairs")
+    return out, reward, group_valid
 
 
 def grid_pairs(n_images: int, k_samples: int, n_subjects: int, device):

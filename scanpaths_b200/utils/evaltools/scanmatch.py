@@ -27,6 +27,7 @@ class ScanMatch(object):
                 raise ValueError('Unknown parameter: %s.' % k)          # scanmatch.py:81
             setattr(self, k, kw[k])
         self._cfg = None
+        self._custom_mask = None
         self.CreateSubMatrix()
         self.GridMask()
 
@@ -36,6 +37,8 @@ class ScanMatch(object):
             self._cfg = S.ScoreConfig(Xres=self.Xres, Yres=self.Yres, Xbin=self.Xbin, Ybin=self.Ybin,
                                       Threshold=self.Threshold, GapValue=self.GapValue, TempBin=self.TempBin,
                                       Offset=self.Offset, stimulus_shape=(self.Yres, self.Xres, 3), dur_scale=1.0)
+            if self._custom_mask is not None:
+                self._cfg.set_mask(self._custom_mask)
         return self._cfg
 
     def CreateSubMatrix(self, Threshold=None):
@@ -73,7 +76,11 @@ class ScanMatch(object):
         return float(out[0, 0].item()), None, None
 
     def maskFromArray(self, array):
-        raise NotImplementedError("custom masks are not supported by the CUDA path")
+        """scanmatch.py:199-200: `array` [Yres, Xres] replaces the grid mask; fixationToSequence then reads the
+        symbol of a fixation from it (K1 takes the table through spb_score_cfg.d_mask)."""
+        self.mask = array
+        self._custom_mask = np.asarray(array)
+        self._config().set_mask(self._custom_mask)
 
     def subMatrixFromArray(self, array):
         self.SubMarix = array                                            # reference typo kept: it has no effect there either

@@ -45,6 +45,18 @@ def _pack_humans(gt_fix_vectors, cfg):
     return S.pack_paths(paths, cfg), np.array(base, dtype=np.int64), np.array(sizes, dtype=np.int64)
 
 
+class _Scored:
+    """One scored call: device score table + both packs + the pair map (host and device copies)."""
+
+    def __init__(self, scores, hpack, ppack, pair_h, pair_s, sizes, d_pair_h, d_pair_s):
+        self.scores, self.hpack, self.ppack = scores, hpack, ppack
+        self.pair_h, self.pair_s, self.sizes = pair_h, pair_s, sizes
+        self.d_pair_h, self.d_pair_s = d_pair_h, d_pair_s
+
+    def __iter__(self):          # (scores, hpack, ppack, pair_h, pair_s, sizes)
+        return iter((self.scores, self.hpack, self.ppack, self.pair_h, self.pair_s, self.sizes))
+
+
 def _score_lists(gt_fix_vectors, predict_fix_vectors, device=None):
     cfg = _eval_cfg(device)
     preds = []
@@ -59,9 +71,10 @@ def _score_lists(gt_fix_vectors, predict_fix_vectors, device=None):
     offs = np.concatenate([np.arange(s) for s in sizes]) if len(sizes) else np.zeros(0, np.int64)
     pair_h = np.repeat(base, sizes) + offs
     dev = cfg.device
-    scores = S.score_pairs(hpack, ppack, torch.from_numpy(pair_h.astype(np.int32)).to(dev),
-                           torch.from_numpy(pair_s.astype(np.int32)).to(dev), cfg)
-    return scores, hpack, ppack, pair_h, pair_s, sizes
+    d_ph = torch.from_numpy(pair_h.astype(np.int32)).to(dev)
+    d_ps = torch.from_numpy(pair_s.astype(np.int32)).to(dev)
+    scores = S.score_pairs(hpack, ppack, d_ph, d_ps, cfg)
+    return _Scored(scores, hpack, ppack, pair_h, pair_s, sizes, d_ph, d_ps)
 
 
 def _metric_dicts(scores, last_group):
@@ -143,18 +156,22 @@ def pairs_eval(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None, 
                is_eliminating_nan=True):
     """OSIE/utils/evaluation.py:284-340 -> [N, 11] (float32 values).  The two ScanMatch
     arguments are accepted for signature compatibility; the drivers' fixed
-    configuration (train.py:201-203) is used."""
-    scores, hpack, ppack, pair_h, pair_s, sizes = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    configuration (train.py:201-203) is used.  Slots 0..4 (MultiMatch, out of scope) hold the
+    placeholder 0.0 wherever the reference returns numbers, and the row is all-NaN exactly where the
+    reference's is (no pair of the image survives the < 3 fixations rule) -- so train.py:237's
+    `np.any(np.isnan(metrics_reward))` rejects the same trials as with the reference."""
+    scored = _score_lists(gt_fix_vectors, predict_fix_vectors)
+    scores, hpack, ppack, pair_h, pair_s, sizes = scored
     S_ = int(sizes[0]) if len(sizes) else 0
     if len(sizes) and not np.all(sizes == S_):
         return _pairs_eval_ragged(scores, hpack, ppack, pair_h, pair_s, sizes, is_eliminating_nan)
-    dev = scores.device
-    ph = torch.from_numpy(pair_h).to(dev); ps = torch.from_numpy(pair_s).to(dev)
-    valid = ((hpack.len.long()[ph] >= MIN_LEN_VALID) & (ppack.len.long()[ps] >= MIN_LEN_VALID)).to(torch.uint8)
-    table, _ = S.reduce_pairs_eval(scores, S_, valid if is_eliminating_nan else valid)
+    table, _, _ = S.reduce_pairs(scores, S_, pair_h=scored.d_pair_h, pair_s=scored.d_pair_s, len_h=hpack.len,
+                                 len_s=ppack.len,
+                                 min_len_valid=MIN_LEN_VALID)
     out = table.cpu().numpy().astype(np.float64)
-    if not is_eliminating_nan:      # a NaN row poisons the sums in the reference (:326-335)
-        bad = (valid.reshape(-1, S_) == 0).any(1).cpu().numpy()
+    if not is_eliminating_nan:      # without elimination one NaN row poisons the image's sums (:326-335)
+        hl, pl = hpack.len.cpu().numpy(), ppack.len.cpu().numpy()
+        bad = ((hl[pair_h] < MIN_LEN_VALID) | (pl[pair_s] < MIN_LEN_VALID)).reshape(-1, S_).any(1)
         out[bad] = np.nan
     return out
 
@@ -169,6 +186,7 @@ def _pairs_eval_ragged(scores, hpack, ppack, pair_h, pair_s, sizes, is_eliminati
         v = np.full(11, np.nan)
         if ok.any() and (is_eliminating_nan or ok.all()):
             r = rows[ok]
+            v[:5] = 0.0
             v[5], v[6], v[7], v[8] = (r[:, 1].sum() / s, r[:, 0].sum() / s, r[:, 2].sum() / s, r[:, 3].sum() / s)
             v[9], v[10] = r[:, 2].min(), r[:, 3].max()
             v = v.astype(np.float32).astype(np.float64)

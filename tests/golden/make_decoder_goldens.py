@@ -17,8 +17,8 @@ from scanpaths_b200.weights import random_state_dict, synthetic_features  # noqa
 CASES = {
     # name: (task, n_images, steps, weight seed, feature seed, bias_std)
     "osie": ("OSIE", 2, 16, 0, 0, 0.02),
-    "air": ("AiR", 1, 6, 1, 1, 0.02),
-    "coco": ("COCO_Search18", 3, 4, 2, 2, 0.02),
+    "air": ("AiR", 2, 16, 1, 1, 0.02),
+    "coco": ("COCO_Search18", 3, 16, 2, 2, 0.02),
 }
 COCO_TASKS = [3, 17, 3]
 

@@ -88,5 +88,55 @@ def test_pipeline_coco_tasks_and_host_input():
     pipe.sampler._calls = 0                                # same Philox streams again
     b = pipe.run(vf.pin_memory(), att.pin_memory(), tasks, keep_scores=True)
     assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["table"][..., 5:], b["table"][..., 5:])
-    assert torch.isnan(a["table"][..., :5]).all()           # MultiMatch slots are out of scope
-    assert torch.isfinite(a["reward"]).all()
+    ok = a["group_valid"].bool()
+    assert (a["table"][ok][:, :5] == 0).all()               # MultiMatch slots: placeholder (out of scope)
+    assert torch.isnan(a["table"][~ok]).all() and torch.isnan(a["reward"][~ok]).all()
+    assert torch.isfinite(a["reward"][ok]).all()
+
+
+def test_pipeline_ragged_subject_counts_and_new_humans():
+    """Images with fewer subjects (pack_subject_lists pads them with empty scanpaths): the padded subjects enter
+    neither the table nor the reward nor the aggregate, and the table divides by the real count (len(gt),
+    OSIE/utils/evaluation.py:329).  A second set_humans() with another subject count must not reuse a pair map."""
+    from oracle import scoring as O
+    from golden.make_goldens import to_struct
+    from scanpaths_b200 import scoring as S
+    N, K, T = 4, 3, 6
+    pipe, vf, att, hx, hl = _setup("OSIE", N, K, 7, T, wave=4)
+    counts = [7, 3, 5, 1]
+    lists = [[to_struct(hx[i, s, :hl[i, s]]) for s in range(counts[i])] for i in range(N)]
+    xyd, lens, nsub = S.pack_subject_lists(lists)
+    assert tuple(xyd.shape[:2]) == (N, 7) and nsub.tolist() == counts
+    pipe.set_humans(xyd, lens, nsub)
+    out = pipe.run(vf.cuda(), keep_paths=True)
+    torch.cuda.synchronize()
+    (hd, n0, n1, smp), = out["paths"]
+    p_xyd, p_len = smp["xyd"].cpu().numpy(), smp["len"].cpu().numpy()
+    rows, best = [], []
+    for k in range(K):
+        preds = [to_struct(p_xyd[k * N + i, :p_len[k * N + i]]) for i in range(N)]
+        pe = O.pairs_eval(lists, preds)
+        tab = out["table"][0, k].cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(tab[:, 5:], pe[:, 5:], rtol=1e-6, equal_nan=True)
+        assert np.array_equal(np.isnan(tab[:, 0]), np.isnan(pe[:, 5]))
+        assert np.array_equal(out["group_valid"][0, k].cpu().numpy() == 0, np.isnan(pe[:, 5]))
+        for i in range(N):
+            sc = np.array([O.score_pair(O.structured_to_array(g), O.structured_to_array(preds[i])) for g in lists[i]], dtype=np.float64)
+            rows.append(sc); best.append([sc[:, 2].min(), sc[:, 3].max()])
+    allrows, best = np.concatenate(rows, 0), np.array(best)
+    m, s = pipe.metrics(out)
+    assert out["acc"][0, 12].item() == K * sum(counts) and out["acc"][0, 13].item() == K * N
+    assert m["ScanMatch"]["with duration"] == pytest.approx(allrows[:, 0].mean(), rel=1e-10)
+    assert m["VAME"]["SED"] == pytest.approx(allrows[:, 2].mean(), rel=1e-10)
+    assert m["VAME"]["STDE"] == pytest.approx(allrows[:, 3].mean(), rel=1e-10)
+    assert m["VAME"]["SED_best"] == pytest.approx(best[:, 0].mean(), rel=1e-10)
+    assert s["VAME"]["STDE_best"] == pytest.approx(best[:, 1].std(), rel=1e-6, abs=1e-9)
+    # other humans, other subject count: fresh pair map, scores equal a fresh pipeline's
+    hx2, hl2 = hx[:, :2], hl[:, :2]
+    pipe.set_humans(hx2, hl2)
+    pipe.sampler._calls = 0
+    again = pipe.run(vf.cuda(), keep_scores=True)
+    fresh, _, _, _, _ = _setup("OSIE", N, K, 7, T, wave=4)
+    fresh.set_humans(hx2, hl2)
+    ref = fresh.run(vf.cuda(), keep_scores=True)
+    assert torch.equal(again["scores"], ref["scores"]) and again["scores"].shape == (1, K, N, 2, 4)
