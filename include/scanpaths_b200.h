@@ -370,6 +370,13 @@ int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, co
 int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
                   int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream);
 
+/* Compensation of the tensor core's truncating fp32 accumulation (csrc/decoder.cuh): every drained "main"
+ * accumulator x becomes x + x * fix.  Default 5.5e-7 (measured on B200, 32 accumulation steps, mixed-sign
+ * operands); CudaDecoder re-measures it at construction with a probe through spb_wino_gemm (fix = 0) against
+ * an exact float64 product and installs the result here.  Process-wide. */
+float spb_get_acc_trunc_fix(void);
+int spb_set_acc_trunc_fix(float fix);
+
 /* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11.  NCHW [N,C,HW] -> NHWC when `transpose`. */
 int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,
                    int32_t transpose, float scale, spb_stream stream);

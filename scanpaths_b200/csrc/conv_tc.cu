@@ -314,7 +314,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < kHalfPix; ++c) tot[c] = fmaf(tot[c], kAccTruncFix, tot[c]);
+                    for (int c = 0; c < kHalfPix; ++c) tot[c] = fmaf(tot[c], a.trunc_fix, tot[c]);
                 } else {
 #pragma unroll
                     for (int c = 0; c < kHalfPix; c += 24) {
@@ -326,9 +326,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float x0 = __uint_as_float(v0[j]), x1 = __uint_as_float(v1[j]), x2 = __uint_as_float(v2[j]);
-                            tot[c + j] += fmaf(x0, kAccTruncFix, x0);
-                            tot[c + 8 + j] += fmaf(x1, kAccTruncFix, x1);
-                            tot[c + 16 + j] += fmaf(x2, kAccTruncFix, x2);
+                            tot[c + j] += fmaf(x0, a.trunc_fix, x0);
+                            tot[c + 8 + j] += fmaf(x1, a.trunc_fix, x1);
+                            tot[c + 16 + j] += fmaf(x2, a.trunc_fix, x2);
                         }
                     }
                 }
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_constant__ CUtensorMap tmU_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                     float *__restrict__ out, int num_tiles, int nct, int ntb, int cols, int64_t rows_pad,
-                    float inv_scale) {
+                    float inv_scale, float trunc_fix) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = base + wg::kStages * wg::kStageBytes;
@@ -568,7 +568,7 @@ wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const float mm = __uint_as_float(vm[e >> 3][e & 7]);
-                        const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, fmaf(mm, kAccTruncFix, mm));
+                        const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, fmaf(mm, trunc_fix, mm));
                         if (i == 0) sa[c + e] = m;
                         else if (i == 1) { sa[c + e] += m; sb[c + e] = m; }
                         else if (i == 2) { sa[c + e] += m; sb[c + e] -= m; }
@@ -652,8 +652,10 @@ static int make_map_out(CUtensorMap *m, float *ptr, int64_t ldo, int64_t rows, i
 
 }  // namespace tc
 
-int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s) {
+int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
     using namespace tc;
+    ConvGemmArgs a = a_in;
+    a.trunc_fix = acc_trunc_fix();
     // ks = 1 / 3 / 5: convolution over 30 x 40 images, operand pairs x = hi + lo / 2^11; with ks = 1 an "image" may
     // be any multiple of 240 rows (plain batched GEMM: out[b][row][col] = sum_k a[b][row][k] w[base_b + col][k])
     const int rows = a.rows_per_img;
@@ -741,7 +743,7 @@ int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, con
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
     wino_gemm_tc_kernel<<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb, cols,
-                                                              rows_pad, inv_scale);
+                                                              rows_pad, inv_scale, acc_trunc_fix());
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }

@@ -998,6 +998,19 @@ static int conv_gemm(const ConvGemmArgs &a, bool tc, cudaStream_t s) {
 
 using namespace spb;
 
+namespace spb {
+static float g_acc_trunc_fix = kAccTruncFixDefault;
+float acc_trunc_fix() { return g_acc_trunc_fix; }
+}  // namespace spb
+
+extern "C" float spb_get_acc_trunc_fix(void) { return g_acc_trunc_fix; }
+
+extern "C" int spb_set_acc_trunc_fix(float fix) {
+    SPB_CHECK_ARG(fix >= 0.0f && fix < 1e-4f, "the accumulator truncation compensation must lie in [0, 1e-4)");
+    g_acc_trunc_fix = fix;
+    return SPB_OK;
+}
+
 extern "C" int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t n_heads, int32_t steps) {
     if (n_images <= 0 || n_streams <= 0 || n_heads <= 0 || steps <= 0) return 0;
     return carve(nullptr, n_images, n_streams, n_heads, steps).bytes;

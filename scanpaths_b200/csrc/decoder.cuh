@@ -12,11 +12,15 @@ constexpr int kGateCols = 4 * kE;   // i, f, o, g
 constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
 // The tensor core adds into its fp32 accumulator with truncation toward zero.  Over the 32 k-steps a
 // "main" accumulator lives (one filter tap / one Winograd position) that shrinks the result by a factor
-// measured on B200 as 1 - 5.5e-7 (scratch/bias_probe.py: -5.36e-7 .. -5.52e-7 for every kernel of this file
-// and every input distribution with mixed-sign weights; -2.6e-6 if all terms have one sign).  Unlike
-// rounding noise this bias is coherent over all outputs and steps -- it made the decode error grow linearly
-// with the step count -- so the drain warps multiply it back: x += x * kAccTruncFix.
-constexpr float kAccTruncFix = 5.5e-7f;
+// measured on B200 as 1 - 5.5e-7 for mixed-sign operands (scratch/bias_probe.py: -5.36e-7 .. -5.52e-7 for
+// every kernel of conv_tc.cu; up to -2.6e-6 if every product has the same sign -- pinned by
+// tests/test_gpu_decoder.py::test_acc_trunc_fix_validity_range).  Unlike rounding noise this bias is coherent
+// over all outputs and steps -- it made the decode error grow linearly with the step count -- so the drain
+// warps multiply it back: x += x * fix.  The factor is a run-time value: the default below, re-measured on
+// the device at decoder construction by a probe GEMM (models/baseline_attention.py::calibrate_acc_trunc_fix)
+// so that another SKU / driver with a different accumulation cannot silently shift parity.
+constexpr float kAccTruncFixDefault = 5.5e-7f;
+float acc_trunc_fix();                 // current value (spb_set_acc_trunc_fix)
 
 // One implicit-GEMM convolution:  out[(n*1200+p)*ldo + col] = inv_scale * conv(a, w)[p, col] (+ bias[col])
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
@@ -34,6 +38,7 @@ struct ConvGemmArgs {
     float inv_scale;
     int w_row_div = 1;            // w_row_base is given in units of w_row_div rows
     int rows_per_img = kHW;       // ks = 1 only: any multiple of 240 (the kernel as a plain batched GEMM)
+    float trunc_fix = 0.0f;       // set by conv_gemm_tc from acc_trunc_fix()
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].

@@ -21,42 +21,13 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "score_common.cuh"
 
 namespace spb {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxStrip = 8;                    // columns per lane in registers
 constexpr int kPanelCols = 32 * kMaxStrip;      // 256
-
-struct PairLayout {                             // per-warp shared memory slice (byte offsets)
-    int ax, ay, bx, by, D, W, arun, brun, ased, bsed, ar, ac, br, bc, awr, awc, bwr, bwc, bytes, pitch;
-};
-
-__host__ __device__ inline PairLayout make_layout(int LA, int LB) {
-    PairLayout L;
-    int o = 0;
-    L.pitch = LA | 1;
-    L.ax = o; o += 8 * LA;
-    L.ay = o; o += 8 * LA;
-    L.bx = o; o += 8 * LB;
-    L.by = o; o += 8 * LB;
-    L.D = o; o += 8 * LB * L.pitch;
-    L.W = o; o += 8 * LB * L.pitch;
-    L.arun = o; o += 4 * LA;
-    L.brun = o; o += 4 * LB;
-    L.ased = o; o += 4 * LA;
-    L.bsed = o; o += 4 * LB;
-    L.ar = o; o += LA;
-    L.ac = o; o += LA;
-    L.br = o; o += LB;
-    L.bc = o; o += LB;
-    L.awr = o; o += LA;
-    L.awc = o; o += LA;
-    L.bwr = o; o += LB;
-    L.bwc = o; o += LB;
-    L.bytes = (o + 15) & ~15;
-    return L;
-}
 
 // ---------------------------------------------------------------------------
 // Needleman-Wunsch over one panel of <= 32*C columns.
@@ -472,7 +443,7 @@ reduce_pairs_kernel(spb_reduce_args a) {
 extern "C" int64_t spb_score_workspace_bytes(int64_t max_human_nwd) {
     if (max_human_nwd < 0) max_human_nwd = 0;
     const int64_t per_warp = (max_human_nwd + 2 + 1) & ~(int64_t)1;
-    return per_warp * 8 * 32 * spb::num_sms();               // <= 32 resident warps per SM run this kernel
+    return per_warp * 8 * 64 * spb::num_sms();               // <= 64 pairs in flight per SM (score_pairs_g8.cu)
 }
 
 extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const int32_t *d_pair_h,
@@ -487,6 +458,12 @@ extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *
     if (sim->lmax > spb::kPanelCols) {
         spb::set_error("spb_score_pairs: simulated scanpaths longer than %d fixations are not supported", spb::kPanelCols);
         return SPB_ERR_UNSUPPORTED;
+    }
+    {   // fast path: four pairs per warp (score_pairs_g8.cu); declines long scanpaths and GapValue != 0
+        int handled = 0;
+        const int rc = spb::score_pairs_g8(*human, *sim, d_pair_h, d_pair_s, n_pairs, *cfg, d_scores, d_workspace,
+                                           workspace_bytes, d_err, (cudaStream_t)stream, &handled);
+        if (rc != SPB_OK || handled) return rc;
     }
     const spb::PairLayout L = spb::make_layout(human->lmax, sim->lmax);
     const int ntab_bytes = (cfg->sm.Xbin * cfg->sm.Ybin * 8 + 15) & ~15;

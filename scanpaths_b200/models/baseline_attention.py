@@ -170,6 +170,81 @@ def prepare_weights(sd, task: str, device):
     return t, w
 
 
+_ACC_FIX_DONE = {}
+
+
+def measure_acc_trunc_bias(device, one_signed=False, seed=12345):
+    """Relative shrink of the tensor-core accumulation, measured with a probe through spb_wino_gemm (fix = 0):
+    24 GEMMs [128 x 512] x [512 x 128] on seeded operands, compared with the exact float64 value of what the
+    kernel sums (hi*hi + (hi*lo + lo*hi) / 2^11 of the same fp16 pairs; numpy on the host: no GPU library call).
+    Returns b with  device result ~ (1 - b) * exact.  `one_signed`: all operands >= 0 (the worst case for a
+    truncating accumulator)."""
+    import numpy as np
+    lib = _lib.load()
+    dev = torch.device(device)
+    rng = np.random.default_rng(seed)
+    rows = cols = 128
+    u = rng.standard_normal((24, rows, 512)).astype(np.float32)
+    w = (rng.standard_normal((24 * cols, 512)) * 0.05).astype(np.float32)
+    if one_signed:
+        u, w = np.abs(u), np.abs(w)
+    mx = float(np.abs(w).max())
+    scale = 2.0 ** (5 - math.floor(math.log2(mx)))
+
+    def pair(x):
+        hi = x.astype(np.float16)
+        lo = ((x.astype(np.float64) - hi.astype(np.float64)) * 2048.0).astype(np.float16)
+        return hi, lo
+    u_hi, u_lo = pair(u)
+    w_hi, w_lo = pair((w.astype(np.float64) * scale).astype(np.float32))
+    f = lambda a: a.astype(np.float64)
+    wh, wl = f(w_hi).reshape(24, cols, 512), f(w_lo).reshape(24, cols, 512)
+    m = (np.einsum("prk,pck->prc", f(u_hi), wh)
+         + (np.einsum("prk,pck->prc", f(u_hi), wl) + np.einsum("prk,pck->prc", f(u_lo), wh)) / 2048.0) / scale
+    m = m.reshape(6, 4, rows, cols)                                           # [j][i]
+    ref = np.stack([m[:, 0] + m[:, 1] + m[:, 2], m[:, 1] - m[:, 2] - m[:, 3]], 1).reshape(12, rows, cols)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = [t(x) for x in (u_hi, u_lo, w_hi, w_lo)]
+    out = torch.empty((12, cols // 128, rows, 128), dtype=torch.float32, device=dev)
+    old = lib.spb_get_acc_trunc_fix()
+    _lib.check(lib.spb_set_acc_trunc_fix(0.0), "spb_set_acc_trunc_fix")
+    try:
+        with torch.cuda.device(dev):
+            _lib.check(lib.spb_wino_gemm(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), _lib.ptr(out),
+                                         rows, cols, 1.0 / scale, _lib.current_stream()), "spb_wino_gemm")
+        got = out.permute(0, 2, 1, 3).reshape(12, rows, cols).double().cpu().numpy()
+    finally:
+        lib.spb_set_acc_trunc_fix(old)
+    return 1.0 - float((got * ref).sum() / (ref * ref).sum())
+
+
+def calibrate_acc_trunc_fix(device):
+    """Installs the measured compensation factor (csrc/decoder.cuh) once per process and GPU model.
+    SPB_ACC_TRUNC_FIX=default keeps the built-in 5.5e-7, SPB_ACC_TRUNC_FIX=<number> forces a value."""
+    import os
+    import warnings
+    lib = _lib.load()
+    key = torch.cuda.get_device_name(device)
+    if key in _ACC_FIX_DONE:
+        return _ACC_FIX_DONE[key]
+    env = os.environ.get("SPB_ACC_TRUNC_FIX", "")
+    if env == "default":
+        fix = lib.spb_get_acc_trunc_fix()
+    elif env:
+        fix = float(env)
+    else:
+        b = measure_acc_trunc_bias(device)
+        if not (0.0 <= b < 5e-6):
+            warnings.warn("tensor-core accumulation probe measured a relative bias of %.3e (expected ~5.5e-7 on B200); "
+                          "keeping the default compensation" % b)
+            fix = lib.spb_get_acc_trunc_fix()
+        else:
+            fix = b
+    _lib.check(lib.spb_set_acc_trunc_fix(fix), "spb_set_acc_trunc_fix")
+    _ACC_FIX_DONE[key] = fix
+    return fix
+
+
 class CudaDecoder:
     """Owns the prepared weights and the workspace of one device; runs spb_decode in waves."""
 
@@ -179,6 +254,8 @@ class CudaDecoder:
         self.task, self.steps, self.wave = task, int(steps), int(wave)
         self.device = torch.device(device)
         self.use_tensor_cores = int(use_tensor_cores)     # 0 = SIMT check path (explicit 5x5 layer), 1 = tcgen05 Winograd + composed head, 2 = tcgen05 direct 3x3
+        if self.use_tensor_cores:
+            self.acc_trunc_fix = calibrate_acc_trunc_fix(self.device)
         self.tensors, self.w = prepare_weights(state_dict, task, self.device)
         self.heads = int(self.w.n_heads)
         self._ws, self._ws_n = None, 0

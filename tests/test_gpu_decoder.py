@@ -173,12 +173,25 @@ def test_decode_waves_and_module_api(lib, golden_dir):
     assert rel.max() < RTOL
 
 
+def _record_margin(name, value):
+    """Worst-case parity margins, harvested into DESIGN.md / profiles (written next to the test run)."""
+    import json
+    path = os.path.join(os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                        "gpurun_out", "parity_margins.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        d = json.load(open(path)) if os.path.exists(path) else {}
+        d[name] = value
+        json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("seed,scale", [(11, 1.0), (12, 4.0), (13, 0.25)])
 def test_decode_other_seeds_and_feature_scales(lib, seed, scale):
-    """Seeds without a recorded golden, and feature maps 4x larger / smaller than the calibrated
-    synthetic ones (exercises the operand scaling): every route against the float64 oracle run here
-    on the host (8 steps, 1 image).  With 4x features the logits reach ~5 and the float32 reference
-    itself drifts to ~5e-6 by step 8, so there the bound is relative to the reference's own error."""
+    """Seeds without a recorded golden, and feature maps 4x larger / smaller than the calibrated synthetic ones
+    (exercises the operand scaling): every route against the float64 oracle run here on the host (8 steps,
+    1 image).  The bound is the gate itself, 1e-5, at every scale."""
     from oracle import decoder as OD
     from scanpaths_b200.models.baseline_attention import CudaDecoder
     from scanpaths_b200.weights import random_state_dict, synthetic_features
@@ -191,13 +204,62 @@ def test_decode_other_seeds_and_feature_scales(lib, seed, scale):
         p64 = OD.decode(sd, vf.double(), "OSIE", steps=T)["all_actions_prob"].numpy()
         p32 = OD.decode(sd, vf.float(), "OSIE", steps=T)["all_actions_prob"].double().numpy()
     ref_err = float((np.abs(p32 - p64) / p64).max())
-    bound = max(RTOL, 3.0 * ref_err) if scale > 1 else RTOL
     for mode in (2, 1):                      # tcgen05 direct, tcgen05 Winograd (product path)
         dec = CudaDecoder(sd, "OSIE", T, dev, wave=1, use_tensor_cores=mode)
         probs, _, _, _ = dec.decode(vf.to(dev))
         err = float((np.abs(probs[0].double().cpu().numpy() - p64) / p64).max())
         print("seed %d scale %.2f mode %d: %.2e (float32 reference: %.2e)" % (seed, scale, mode, err, ref_err))
-        assert err < bound, (mode, err, ref_err)
+        _record_margin("T8_seed%d_scale%g_mode%d" % (seed, scale, mode), {"err": err, "ref_f32": ref_err})
+        assert err < RTOL, (mode, err, ref_err)
+
+
+@pytest.mark.parametrize("scale", [1.0, 2.0, 4.0])
+def test_decode_realistic_magnitudes_full_length(lib, scale):
+    """T = 16 at feature magnitudes 1x, 2x and 4x the calibrated synthetic ones (real checkpoints'
+    relu(sal_conv(resnet)) scale is unknown here): the product path against the float64 oracle with the
+    UNRELAXED 1e-5 gate on probabilities, mu and sigma2; the margins are recorded."""
+    from oracle import decoder as OD
+    from scanpaths_b200.models.baseline_attention import CudaDecoder
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    dev = torch.device("cuda")
+    T = 16
+    sd = random_state_dict("OSIE", 21, calibrated=True, bias_std=0.05)
+    vf = synthetic_features(1, 21) * scale
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        r64 = OD.decode(sd, vf.double(), "OSIE", steps=T)
+        r32 = OD.decode(sd, vf.float(), "OSIE", steps=T)
+    rel = lambda a, b: float((np.abs(a - b) / np.abs(b)).max())
+    p64 = r64["all_actions_prob"].numpy()
+    ref_err = rel(r32["all_actions_prob"].double().numpy(), p64)
+    probs, mu, s2, _ = CudaDecoder(sd, "OSIE", T, dev, wave=1, use_tensor_cores=1).decode(vf.to(dev))
+    errs = {"probs": rel(probs[0].double().cpu().numpy(), p64),
+            "mu": rel(mu[0].double().cpu().numpy(), r64["log_normal_mu"].numpy()),
+            "sigma2": rel(s2[0].double().cpu().numpy(), r64["log_normal_sigma2"].numpy()),
+            "ref_f32_probs": ref_err, "max_logit": float(np.log(p64.max() / p64.min()))}
+    per_step = [rel(probs[0, :, t].double().cpu().numpy(), p64[:, t]) for t in range(T)]
+    print("scale %g T=16:" % scale, errs, "per step:", ["%.1e" % e for e in per_step])
+    _record_margin("T16_scale%g_product_path" % scale, {**errs, "per_step": per_step})
+    assert max(errs["probs"], errs["mu"], errs["sigma2"]) < RTOL, errs
+
+
+def test_acc_trunc_fix_validity_range(lib):
+    """Pins the assumption behind the accumulator compensation (csrc/decoder.cuh): over the 32 accumulation
+    steps a main accumulator lives, truncation shrinks a MIXED-SIGN sum by ~5.5e-7 -- the regime of every GEMM
+    of the decode path (weights are mixed-sign, so the products are, whatever the sign of the activations) --
+    and by ~2.6e-6 when every product has one sign (the compensation under-corrects there).  The factor in use
+    is the one measured on this device at decoder construction."""
+    from scanpaths_b200.models import baseline_attention as BA
+    dev = torch.device("cuda")
+    mixed = BA.measure_acc_trunc_bias(dev)
+    mixed2 = BA.measure_acc_trunc_bias(dev, seed=777)
+    signed = BA.measure_acc_trunc_bias(dev, one_signed=True)
+    print("accumulator bias: mixed-sign %.3e / %.3e, one-signed %.3e" % (mixed, mixed2, signed))
+    _record_margin("acc_trunc_bias", {"mixed": mixed, "mixed_other_seed": mixed2, "one_signed": signed})
+    assert 3.5e-7 < mixed < 8e-7 and abs(mixed - mixed2) < 5e-8, (mixed, mixed2)
+    assert 1e-6 < signed < 5e-6, signed
+    fix = BA.calibrate_acc_trunc_fix(dev)
+    assert abs(fix - lib.spb_get_acc_trunc_fix()) < 1e-12 and abs(fix - mixed) < 5e-8
 
 
 def test_decode_full_wave_is_independent_of_batch_layout(lib):
