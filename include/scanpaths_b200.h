@@ -338,8 +338,10 @@ typedef struct spb_decoder_weights {
 
 typedef struct spb_decoder_io {
     int32_t n_images, steps;
-    int32_t use_tensor_cores;        /* 1: tcgen05, Winograd F(2x4,3x3) gate GEMMs + composed head (product path); */
-                                     /* 2: tcgen05 direct 3x3 implicit GEMM + composed head; 0: SIMT fp32 check kernels */
+    int32_t use_tensor_cores;        /* 1 (product path): tcgen05, Winograd F(2x4,3x3) GEMMs for the h-gates, direct */
+                                     /*   implicit GEMM for the loop-invariant x-gates, composed head;                */
+                                     /* 2: direct 3x3 implicit GEMM for both; 3: Winograd for both;                   */
+                                     /* 0: SIMT fp32 check kernels with the explicit 5x5 layer                        */
     int32_t reserved;
     const float *d_vf;               /* [N, 512, 30, 40] visual_feature (NCHW, as the encoder emits it) */
     const float *d_att;              /* [N, 1200] initial attention map, or NULL = zeros (OSIE)         */

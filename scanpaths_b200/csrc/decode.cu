@@ -373,71 +373,112 @@ lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ 
 constexpr int kTilesY = 15, kTilesX = 10, kTilesPerImg = 150;
 constexpr int kWinoPos = 24;        // position p = 4j + i (i: F(2,3) row position, j: F(4,3) column position)
 
-// U[p][n*150 + tile][ci] = (B2^T d B4)[i][j]; one block per (image, tile), thread = 2 channels (the kernel is
-// latency-bound: 2 channels per thread keep it at ~70 registers, i.e. 3 x 8 warps per SM in flight).
-__global__ void __launch_bounds__(256, 3)
+// U[p][n*150 + tile][ci] = (B2^T d B4)[i][j].  One block per (image, tile row), thread = 2 channels, walking the 10
+// tiles of the row: the row half B2^T of the transform is applied to each pixel column once and the two columns a
+// tile shares with its left neighbour stay in registers (16 new pixel loads per tile instead of 24), the loads of
+// the next tile are issued before this tile's column transform and its 48 stores, and a block writes 10 KB
+// contiguous per position plane.  HBM-bound: 2.5 MB read + 7.2 MB written per image.
+__global__ void __launch_bounds__(256, 2)
 wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, __half *__restrict__ u_hi,
                   __half *__restrict__ u_lo, int64_t rows_pad) {
-    const int64_t nt = blockIdx.x;                   // n*150 + tile
-    const int64_t n = nt / kTilesPerImg;
-    const int tile = (int)(nt - n * kTilesPerImg);
-    const int ty = tile / kTilesX, tx = tile - ty * kTilesX;
+    const int64_t n = blockIdx.x / kTilesY;
+    const int ty = (int)(blockIdx.x - n * kTilesY);
     const int c0 = threadIdx.x * 2;
-    // all 48 loads of the 4 x 6 patch are issued before the first use (one memory round trip per block):
-    // out-of-image pixels load from a clamped address and are zeroed afterwards
-    uint32_t rh[4][6], rl[4][6];
+    // rows 2ty-1 .. 2ty+2 of the image: clamped address + validity flag (out-of-image rows are the zero padding)
+    int64_t row_off[4];
+    bool row_in[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a) {
+        const int yy = 2 * ty - 1 + a;
+        row_in[a] = yy >= 0 && yy < kH;
+        row_off[a] = ((n * kH + min(max(yy, 0), kH - 1)) * kW) * (int64_t)kE + c0;
+    }
+    uint32_t rh[4][4], rl[4][4];                     // raw (hi, lo) pairs of the 4 new pixel columns of a tile
+    auto issue = [&](int tx) {                       // columns 4tx+1 .. 4tx+4 (the last one may be x = 40: padding)
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const int yy = min(max(2 * ty - 1 + a, 0), kH - 1), xx = min(max(4 * tx - 1 + b, 0), kW - 1);
-            const int64_t off = ((n * kH + yy) * kW + xx) * (int64_t)kE + c0;
-            rh[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_hi + off));
-            rl[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_lo + off));
-        }
-    float u[4][6][2];
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 6; ++b) {
+            for (int b = 0; b < 4; ++b) {
+                const int xx = min(4 * tx + 1 + b, kW - 1);
+                rh[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_hi + row_off[a] + (int64_t)xx * kE));
+                rl[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_lo + row_off[a] + (int64_t)xx * kE));
+            }
+    };
+    float u[4][6][2];                                // row-transformed columns of the current tile
+    // tile 0: column x = -1 is padding, column x = 0 is loaded here
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i][4][0] = u[i][4][1] = 0.0f;
+    {
         float d[4][2];
-        const int xx = 4 * tx - 1 + b;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const int yy = 2 * ty - 1 + a;
-            const bool in = yy >= 0 && yy < kH && xx >= 0 && xx < kW;
-            const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&rh[a][b]));
-            const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&rl[a][b]));
-            d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
-            d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
+            const uint32_t vh = __ldg(reinterpret_cast<const uint32_t *>(h_hi + row_off[a]));
+            const uint32_t vl = __ldg(reinterpret_cast<const uint32_t *>(h_lo + row_off[a]));
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&vh));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&vl));
+            d[a][0] = row_in[a] ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
+            d[a][1] = row_in[a] ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            u[0][b][e] = d[0][e] - d[2][e];
-            u[1][b][e] = d[1][e] + d[2][e];
-            u[2][b][e] = d[2][e] - d[1][e];
-            u[3][b][e] = d[1][e] - d[3][e];
+            u[0][5][e] = d[0][e] - d[2][e];
+            u[1][5][e] = d[1][e] + d[2][e];
+            u[2][5][e] = d[2][e] - d[1][e];
+            u[3][5][e] = d[1][e] - d[3][e];
         }
     }
+    issue(0);
+    for (int tx = 0; tx < kTilesX; ++tx) {
+        // shift: the previous tile's last two columns are this tile's first two
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float t[6][2];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float d0 = u[i][0][e], d1 = u[i][1][e], d2 = u[i][2][e], d3 = u[i][3][e], d4 = u[i][4][e], d5 = u[i][5][e];
-            t[0][e] = fmaf(4.0f, d0, fmaf(-5.0f, d2, d4));
-            t[1][e] = fmaf(-4.0f, d1 + d2, d3 + d4);
-            t[2][e] = fmaf(4.0f, d1 - d2, d4 - d3);
-            t[3][e] = fmaf(2.0f, d3 - d1, d4 - d2);
-            t[4][e] = fmaf(2.0f, d1 - d3, d4 - d2);
-            t[5][e] = fmaf(4.0f, d1, fmaf(-5.0f, d3, d5));
+            for (int e = 0; e < 2; ++e) { u[i][0][e] = u[i][4][e]; u[i][1][e] = u[i][5][e]; }
+        // row transform of the 4 new columns
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const bool col_in = 4 * tx + 1 + b < kW;
+            float d[4][2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&rh[a][b]));
+                const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&rl[a][b]));
+                const bool in = row_in[a] && col_in;
+                d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
+                d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                u[0][2 + b][e] = d[0][e] - d[2][e];
+                u[1][2 + b][e] = d[1][e] + d[2][e];
+                u[2][2 + b][e] = d[2][e] - d[1][e];
+                u[3][2 + b][e] = d[1][e] - d[3][e];
+            }
         }
+        if (tx + 1 < kTilesX) issue(tx + 1);          // next tile's loads fly during this tile's stores
+        const int64_t nt = n * kTilesPerImg + ty * kTilesX + tx;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            __half hh[2], hl[2];
+        for (int i = 0; i < 4; ++i) {
+            float t[6][2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
-            const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
-            *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
-            *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
+            for (int e = 0; e < 2; ++e) {
+                const float d0 = u[i][0][e], d1 = u[i][1][e], d2 = u[i][2][e], d3 = u[i][3][e], d4 = u[i][4][e], d5 = u[i][5][e];
+                t[0][e] = fmaf(4.0f, d0, fmaf(-5.0f, d2, d4));
+                t[1][e] = fmaf(-4.0f, d1 + d2, d3 + d4);
+                t[2][e] = fmaf(4.0f, d1 - d2, d4 - d3);
+                t[3][e] = fmaf(2.0f, d3 - d1, d4 - d2);
+                t[4][e] = fmaf(2.0f, d1 - d3, d4 - d2);
+                t[5][e] = fmaf(4.0f, d1, fmaf(-5.0f, d3, d5));
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                __half hh[2], hl[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
+                const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
+                *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+                *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
+            }
         }
     }
 }
@@ -670,47 +711,58 @@ head_gather_kernel(const float *__restrict__ z, int ldz, const float *__restrict
     y3[idx] = s3 + b23[set * 2 + 1];
 }
 
-// duration pre-activation of the border windows: one 4-warp block per (image, head, window); the 121
-// taps are dealt round-robin to the warps, lanes split the channels, partial sums meet in smem.
-__global__ void __launch_bounds__(128)
+// duration pre-activation of the border windows: one block per (window, head, group of 4 images) with 16 warps =
+// 4 images x 4 tap groups; lanes split the channels.  The four warps of a tap group walk the same taps at the same
+// time, so the 248 KB of composed weights of a window come from L2 once per 4 images (L1 serves the other three) --
+// the first version (one block per image and window) re-read them for every image and was L2-bandwidth-bound.
+constexpr int kDrtImgs = 4, kDrtTapGroups = 4;
+
+__global__ void __launch_bounds__(kDrtImgs * kDrtTapGroups * 32)
 head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ wd_eff,
-                const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD,
+                const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD, int64_t n_images,
                 float *__restrict__ drt_pre) {
-    __shared__ float part[4];
+    __shared__ float part[kDrtTapGroups][kDrtImgs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int img = warp % kDrtImgs, tg = warp / kDrtImgs;
     // only the 13 windows of the top row / left column run here (their composed kernels differ: 3 border
     // variants); the 35 interior windows are gathered from the head GEMM by head_drt_gather_kernel
     const int bi = (int)(blockIdx.x % 13);
     const int o = bi < 8 ? bi : (bi - 7) * 8;
-    const int64_t nh = blockIdx.x / 13;
-    const int64_t win = nh * 48 + o;                  // (n*HD + hd)*48 + o
-    const int64_t n = nh / HD;
-    const int hd = (int)(nh % HD);
-    const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
+    const int hd = (int)((blockIdx.x / 13) % HD);
+    const int64_t n = (int64_t)(blockIdx.x / (13 * HD)) * kDrtImgs + img;
+    const bool live = n < n_images;
+    const int64_t nc = live ? n : n_images - 1;
+    const int set = (w_row_base ? w_row_base[nc] / kE : 0) + hd;
     const int oy = o / 8, ox = o % 8;
     const int variant = 2 * (oy == 0) + (ox == 0);
     const float *wv = wd_eff + ((int64_t)set * 4 + variant) * 121 * kE;
-    float acc = 0.0f;
-    for (int tap = warp; tap < 121; tap += 4) {
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int tap = tg; tap < 121; tap += kDrtTapGroups) {
         const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
         if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
-        const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float hv[8];
-            load_h8(h_hi, h_lo, base + 256 * j, hv);
-            const float4 *wq = reinterpret_cast<const float4 *>(wv + tap * kE + lane * 8 + 256 * j);
-            const float4 w0 = wq[0], w1 = wq[1];
-            acc = fmaf(hv[0], w0.x, acc); acc = fmaf(hv[1], w0.y, acc);
-            acc = fmaf(hv[2], w0.z, acc); acc = fmaf(hv[3], w0.w, acc);
-            acc = fmaf(hv[4], w1.x, acc); acc = fmaf(hv[5], w1.y, acc);
-            acc = fmaf(hv[6], w1.z, acc); acc = fmaf(hv[7], w1.w, acc);
+        const int64_t base = ((nc * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
+        float h0[8], h1[8];
+        load_h8(h_hi, h_lo, base, h0);
+        load_h8(h_hi, h_lo, base + 256, h1);
+        const float4 *wq = reinterpret_cast<const float4 *>(wv + tap * kE + lane * 8);
+        const float4 w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 64), w3 = __ldg(wq + 65);
+        acc0 = fmaf(h0[0], w0.x, acc0); acc0 = fmaf(h0[1], w0.y, acc0); acc0 = fmaf(h0[2], w0.z, acc0); acc0 = fmaf(h0[3], w0.w, acc0);
+        acc0 = fmaf(h0[4], w1.x, acc0); acc0 = fmaf(h0[5], w1.y, acc0); acc0 = fmaf(h0[6], w1.z, acc0); acc0 = fmaf(h0[7], w1.w, acc0);
+        acc1 = fmaf(h1[0], w2.x, acc1); acc1 = fmaf(h1[1], w2.y, acc1); acc1 = fmaf(h1[2], w2.z, acc1); acc1 = fmaf(h1[3], w2.w, acc1);
+        acc1 = fmaf(h1[4], w3.x, acc1); acc1 = fmaf(h1[5], w3.y, acc1); acc1 = fmaf(h1[6], w3.z, acc1); acc1 = fmaf(h1[7], w3.w, acc1);
+    }
+    float acc = acc0 + acc1;
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) part[tg][img] = acc;
+    __syncthreads();
+    if (threadIdx.x < kDrtImgs) {
+        const int64_t n2 = (int64_t)(blockIdx.x / (13 * HD)) * kDrtImgs + threadIdx.x;
+        if (n2 < n_images) {
+            const int set2 = (w_row_base ? w_row_base[n2] / kE : 0) + hd;
+            drt_pre[(n2 * HD + hd) * 48 + o] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) +
+                                                (part[2][threadIdx.x] + part[3][threadIdx.x])) + bd_eff[set2 * 4 + variant];
         }
     }
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) part[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) drt_pre[win] = ((part[0] + part[1]) + (part[2] + part[3])) + bd_eff[set * 4 + variant];
 }
 
 // duration pre-activation of the 35 interior windows from the head GEMM: Z[p][kDrtCol0 + tap] = h[p,:] . wd_eff[set][0][tap,:],
@@ -1075,7 +1127,13 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     }
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = io->use_tensor_cores != 0;
-    const bool wino = io->use_tensor_cores == 1;       // 1: Winograd gate GEMMs (product path); 2: direct 3x3 GEMM
+    // 1 (product path): Winograd F(2x4,3x3) GEMMs for the h-gates (every step), direct implicit GEMM for the
+    //    loop-invariant x-gates -- their error is added to the pre-activations of ALL steps, i.e. it is coherent
+    //    over the recurrence, and the Winograd form's is 2x larger (fp32 accumulation noise amplified by the
+    //    output transform): measured end to end, Winograd x-gates double the error of the probabilities;
+    // 2: direct implicit GEMM for both;  3: Winograd for both (the round-1 product path, kept for comparison)
+    const bool wino = io->use_tensor_cores == 1 || io->use_tensor_cores == 3;
+    const bool wino_x = io->use_tensor_cores == 3;
     const int64_t NP = N * kHW;
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
@@ -1085,9 +1143,9 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     SPB_LAUNCH_CHECK();
     prof_end(s);
     prof_begin(kTagConvX, s);
-    if (wino) {
+    if (wino_x) {
         // the loop-invariant x-gate convolution through the same Winograd F(2x4,3x3) kernels as the h-gates
-        wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
+        wino_input_kernel<<<(unsigned)(N * kTilesY), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
         SPB_LAUNCH_CHECK();
         SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->wwx_hi, (const __half *)w->wwx_lo, ws.wm, ws.rows_pad,
                              kGateCols, w->inv_scale_wx, s));
@@ -1164,7 +1222,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             // on tcgen05, output transform folded into the ConvLSTM cell.  h(0) = 0 -> nothing to multiply.
             if (t > 0) {
                 prof_begin(kTagWinoIn, s);
-                wino_input_kernel<<<(unsigned)(N * kTilesPerImg), 256, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
+                wino_input_kernel<<<(unsigned)(N * kTilesY), 256, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
                                                                              ws.rows_pad);
                 SPB_LAUNCH_CHECK();
                 prof_end(s);
@@ -1221,8 +1279,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             head_gather_kernel<<<(unsigned)((N * HD * kHW + 255) / 256), 256, 0, s>>>(
                 ws.z23, HD * kHeadCols, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3, N * HD * kHW);
             SPB_LAUNCH_CHECK();
-            head_drt_kernel<<<(unsigned)(N * HD * 13), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
-                                                                   io->d_w_row_base, HD, ws.drt_pre);
+            head_drt_kernel<<<(unsigned)((N + kDrtImgs - 1) / kDrtImgs * HD * 13), kDrtImgs * kDrtTapGroups * 32, 0, s>>>(
+                ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff, io->d_w_row_base, HD, N, ws.drt_pre);
             SPB_LAUNCH_CHECK();
             head_drt_gather_kernel<<<(unsigned)((N * HD * 35 * 32 + 255) / 256), 256, 0, s>>>(
                 ws.z23, HD * kHeadCols, w->bd_eff, io->d_w_row_base, HD, ws.drt_pre, N * HD * 35);

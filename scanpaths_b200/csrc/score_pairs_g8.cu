@@ -23,8 +23,8 @@ namespace spb {
 constexpr int kG = 8;                     // lanes per pair
 constexpr int kPairsPerWarp = 32 / kG;
 constexpr int kG8Warps = 4;               // warps per block -> 16 pairs per block
-constexpr int kWdC = 8;                   // with-duration columns per lane
-constexpr int kWdPanel = kG * kWdC;       // 64
+constexpr int kWdC = 16;                  // with-duration columns per lane, at most (the warp uses ceil(m / 8))
+constexpr int kWdPanel = kG * kWdC;       // 128
 
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -90,6 +90,82 @@ __device__ __forceinline__ double nw_panel_g8(const uint8_t *ar, const uint8_t *
     const int cm = nl > 0 ? (pcols - 1) - (nl - 1) * C : 0;
 #pragma unroll
     for (int c = 0; c < C; ++c)
+        if (c == cm) res = prev[c];
+    return __shfl_sync(0xffffffffu, res, nl > 0 ? nl - 1 : 0, kG);
+}
+
+// The with-duration strings (run-length coded: ~10 runs of ~5 symbols) -- >80 % of all cell updates.
+//   * the substitution score of a cell depends only on (human run, simulated run): a per-pair table
+//     S[u][v] in shared memory (it aliases the STDE tile W, which is initialised later) turns the lookup
+//     into one LDS at (row base + a per-column constant);
+//   * every lane owns `cw` consecutive columns, cw = ceil(longest string of the warp's four pairs / 8) <= 16
+//     (warp-uniform: the unrolled strip skips the cells >= cw with a uniform branch), so a 50-symbol string
+//     costs 7 cells per step and an 80-symbol one 10 -- not two 64-column panels;
+//   * the recurrence is evaluated in two phases: t = F[i-1][j-1] + s and m = max(t, F[i-1][j]) only read the
+//     previous row (independent across the strip), then v = max(m, F[i][j-1]) is a running maximum -- the same
+//     three operands per cell as scanmatch.py:146-148, bit-identical, with a dependent chain of one max per cell;
+//   * the run counter advances branch-free.
+__device__ __forceinline__ double nw_wd_g8(const double *S, int spitch, const int *arun, int n, const int *brun,
+                                           int nb_runs, int col0, int pcols, int cw, bool active, bool more_panels,
+                                           double *bnd, int gl) {
+    const int nl = active ? (pcols + cw - 1) / cw : 0;        // lanes of the group that own columns
+    const int j0 = col0 + gl * cw;
+    int voff[kWdC];                                           // simulated run of each of my columns
+    {
+        int acc = 0, r = 0;
+#pragma unroll
+        for (int c = 0; c < kWdC; ++c) {
+            voff[c] = 0;
+            if (c < cw && gl < nl) {
+                const int j = min(j0 + c, col0 + pcols - 1);  // columns past the end repeat the last symbol
+                while (r < nb_runs - 1 && acc + brun[r] <= j) { acc += brun[r]; ++r; }
+                voff[c] = r;
+            }
+        }
+    }
+    const int steps_w = warp_max(nl > 0 ? n + nl - 1 : 0);
+    double prev[kWdC];
+#pragma unroll
+    for (int c = 0; c < kWdC; ++c) prev[c] = 0.0;
+    double leftPrev = 0.0, myLast = 0.0;
+    int ri = 0, rem = n == 0 ? 1 : arun[0];
+    for (int t = 0; t < steps_w; ++t) {
+        const double recv = __shfl_up_sync(0xffffffffu, myLast, 1, kG);
+        const int i = t - gl;
+        if (i >= 0 && i < n && gl < nl) {
+            const double leftCur = (gl == 0) ? (col0 == 0 ? 0.0 : bnd[i + 1]) : recv;
+            const double *Sr = S + ri * spitch;
+            double mm[kWdC];
+            double d = leftPrev;
+#pragma unroll
+            for (int c = 0; c < kWdC; ++c)
+                if (c < cw) {                                               // warp-uniform
+                    const double tt = d + Sr[voff[c]];                      // F[i-1][j-1] + s
+                    d = prev[c];
+                    mm[c] = fmax(tt, d);                                    // | F[i-1][j]
+                }
+            double l = leftCur;
+#pragma unroll
+            for (int c = 0; c < kWdC; ++c)
+                if (c < cw) {
+                    l = fmax(mm[c], l);                                     // | F[i][j-1]
+                    prev[c] = l;
+                }
+            leftPrev = leftCur;
+            myLast = l;
+            if (more_panels && gl == kG - 1) bnd[i + 1] = l;                // a full panel: its last column feeds the next one
+            --rem;                                                          // next row: advance the human run, branch-free
+            const int adv = rem == 0 ? 1 : 0;
+            ri += adv;
+            const int nxt = arun[min(ri, n - 1)];                           // (runs <= symbols: always inside the slice)
+            rem = adv ? ((i + 1 < n) ? nxt : 1) : rem;
+        }
+    }
+    // F[n][col0 + pcols]: strip position of the last column in the last lane that owns columns
+    double res = 0.0;
+    const int cm = nl > 0 ? (pcols - 1) - (nl - 1) * cw : 0;
+#pragma unroll
+    for (int c = 0; c < kWdC; ++c)
         if (c == cm) res = prev[c];
     return __shfl_sync(0xffffffffu, res, nl > 0 ? nl - 1 : 0, kG);
 }
@@ -274,7 +350,7 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
         }
         // ---- SED
         const int sed = lev_g8<LC>(ased, La, bsed, Lb, gl);
-        // ---- ScanMatch with duration: run-length strings, 64-column panels
+        // ---- ScanMatch with duration: run-length strings
         double wd = nan("");
         {
             bool act = n_wd > 0 && m_wd > 0;
@@ -282,6 +358,20 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
                 if (gl == 0) atomicExch(err, 1);
                 act = false;
             }
+            // substitution table of the pair: S[human run][simulated run] (aliases W, pitch = simulated lmax)
+            double *S = W;
+            const int spitch = B.lmax;
+            const int ntab_w = warp_max(act ? na_runs * nb_runs : 0);
+            for (int e0 = 0; e0 < ntab_w; e0 += kG) {
+                const int e = e0 + gl;
+                if (act && e < na_runs * nb_runs) {
+                    const int u = e / nb_runs, v = e - u * nb_runs;
+                    S[u * spitch + v] = subd[abs((int)awr[u] - (int)bwr[v]) * xbin + abs((int)awc[u] - (int)bwc[v])];
+                }
+            }
+            __syncwarp();
+            const int m_w = warp_max(act ? min(m_wd, kWdPanel) : 0);
+            const int cw = (m_w + kG - 1) / kG;                      // columns per lane, warp-uniform, <= 16
             const int npan = act ? (m_wd + kWdPanel - 1) / kWdPanel : 0;
             const int npan_w = warp_max(npan);
             double corner = 0.0;
@@ -289,8 +379,7 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
                 const bool on = pn < npan;
                 const int col0 = pn * kWdPanel;
                 const int pcols = on ? min(kWdPanel, m_wd - col0) : 0;
-                const double c = nw_panel_g8<kWdC, false>(awr, awc, arun, n_wd, bwr, bwc, brun, nb_runs, col0, pcols, on,
-                                                          pn + 1 < npan, subd, xbin, bnd, gl);
+                const double c = nw_wd_g8(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, cw, on, pn + 1 < npan, bnd, gl);
                 if (on) corner = c;
                 __syncwarp();
             }

@@ -87,7 +87,8 @@ def test_pipeline_coco_tasks_and_host_input():
     a = pipe.run(vf.cuda(), att.cuda(), tasks, keep_scores=True)
     pipe.sampler._calls = 0                                # same Philox streams again
     b = pipe.run(vf.pin_memory(), att.pin_memory(), tasks, keep_scores=True)
-    assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["table"][..., 5:], b["table"][..., 5:])
+    assert torch.equal(a["scores"], b["scores"])
+    assert torch.equal(torch.nan_to_num(a["table"], nan=-1.0), torch.nan_to_num(b["table"], nan=-1.0))
     ok = a["group_valid"].bool()
     assert (a["table"][ok][:, :5] == 0).all()               # MultiMatch slots: placeholder (out of scope)
     assert torch.isnan(a["table"][~ok]).all() and torch.isnan(a["reward"][~ok]).all()

@@ -153,8 +153,10 @@ def test_scst_step_rewards_match_oracle_and_reject_short_trials(data):
     from scanpaths_b200.scst import ScstRewardStep
     g, s, dev, _ = data
     N, K = 4, 5
-    probs = torch.tensor(g["probs"][:N], device=dev, requires_grad=True)     # image 1 stops at step 3 for sure,
-    mu = torch.tensor(g["mu"][:N], device=dev, requires_grad=True)           # often earlier: short scanpaths
+    p_np = g["probs"][:N].copy()
+    p_np[1, 1] *= 0.7 / (1.0 - p_np[1, 1, 0]); p_np[1, 1, 0] = 0.3           # image 1 stops after ONE fixation in ~30 % of
+    probs = torch.tensor(p_np, device=dev, requires_grad=True)               # the trials: those trials must be rejected
+    mu = torch.tensor(g["mu"][:N], device=dev, requires_grad=True)
     s2 = torch.tensor(g["sigma2"][:N], device=dev, requires_grad=True)
     humans = _humans(N, 5, 3, short={(0, 1)})
     step = ScstRewardStep(Sampling(convLSTM_length=16, min_length=1, seed=5), dev, rl_sample_number=K, spare=3)
