@@ -520,11 +520,17 @@ def scst_record(args, dev, lib, cpu):
         loss, aux = step(pr[0], mm[0], ss[0])
         return loss
 
+    def with_graphed_decode():                            # the 16-step rollout replayed from one CUDA graph
+        pr, mm, ss, _ = dec.decode_graphed(vf)
+        loss, aux = step(pr[0], mm[0], ss[0])
+        return loss
+
     res = {}
     l0 = lib.spb_kernel_launches()
     reward_only(); torch.cuda.synchronize()
     res["launches_reward_step"] = int(lib.spb_kernel_launches() - l0)
-    for name, fn, reps in (("reward_sample_score_loss_backward", reward_only, 50), ("decode_plus_reward", with_decode, 10)):
+    for name, fn, reps in (("reward_sample_score_loss_backward", reward_only, 50), ("decode_plus_reward", with_decode, 10),
+                           ("graphed_decode_plus_reward", with_graphed_decode, 20)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

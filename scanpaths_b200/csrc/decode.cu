@@ -711,58 +711,47 @@ head_gather_kernel(const float *__restrict__ z, int ldz, const float *__restrict
     y3[idx] = s3 + b23[set * 2 + 1];
 }
 
-// duration pre-activation of the border windows: one block per (window, head, group of 4 images) with 16 warps =
-// 4 images x 4 tap groups; lanes split the channels.  The four warps of a tap group walk the same taps at the same
-// time, so the 248 KB of composed weights of a window come from L2 once per 4 images (L1 serves the other three) --
-// the first version (one block per image and window) re-read them for every image and was L2-bandwidth-bound.
-constexpr int kDrtImgs = 4, kDrtTapGroups = 4;
-
-__global__ void __launch_bounds__(kDrtImgs * kDrtTapGroups * 32)
+// duration pre-activation of the border windows: one 4-warp block per (image, head, window); the 121
+// taps are dealt round-robin to the warps, lanes split the channels, partial sums meet in smem.
+__global__ void __launch_bounds__(128)
 head_drt_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, const float *__restrict__ wd_eff,
-                const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD, int64_t n_images,
+                const float *__restrict__ bd_eff, const int32_t *__restrict__ w_row_base, int HD,
                 float *__restrict__ drt_pre) {
-    __shared__ float part[kDrtTapGroups][kDrtImgs];
+    __shared__ float part[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int img = warp % kDrtImgs, tg = warp / kDrtImgs;
     // only the 13 windows of the top row / left column run here (their composed kernels differ: 3 border
     // variants); the 35 interior windows are gathered from the head GEMM by head_drt_gather_kernel
     const int bi = (int)(blockIdx.x % 13);
     const int o = bi < 8 ? bi : (bi - 7) * 8;
-    const int hd = (int)((blockIdx.x / 13) % HD);
-    const int64_t n = (int64_t)(blockIdx.x / (13 * HD)) * kDrtImgs + img;
-    const bool live = n < n_images;
-    const int64_t nc = live ? n : n_images - 1;
-    const int set = (w_row_base ? w_row_base[nc] / kE : 0) + hd;
+    const int64_t nh = blockIdx.x / 13;
+    const int64_t win = nh * 48 + o;                  // (n*HD + hd)*48 + o
+    const int64_t n = nh / HD;
+    const int hd = (int)(nh % HD);
+    const int set = (w_row_base ? w_row_base[n] / kE : 0) + hd;
     const int oy = o / 8, ox = o % 8;
     const int variant = 2 * (oy == 0) + (ox == 0);
     const float *wv = wd_eff + ((int64_t)set * 4 + variant) * 121 * kE;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    for (int tap = tg; tap < 121; tap += kDrtTapGroups) {
+    float acc = 0.0f;
+    for (int tap = warp; tap < 121; tap += 4) {
         const int yy = 5 * oy - 4 + tap / 11, xx = 5 * ox - 4 + tap % 11;
         if (yy < 0 || yy >= kH || xx < 0 || xx >= kW) continue;
-        const int64_t base = ((nc * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
-        float h0[8], h1[8];
-        load_h8(h_hi, h_lo, base, h0);
-        load_h8(h_hi, h_lo, base + 256, h1);
-        const float4 *wq = reinterpret_cast<const float4 *>(wv + tap * kE + lane * 8);
-        const float4 w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 64), w3 = __ldg(wq + 65);
-        acc0 = fmaf(h0[0], w0.x, acc0); acc0 = fmaf(h0[1], w0.y, acc0); acc0 = fmaf(h0[2], w0.z, acc0); acc0 = fmaf(h0[3], w0.w, acc0);
-        acc0 = fmaf(h0[4], w1.x, acc0); acc0 = fmaf(h0[5], w1.y, acc0); acc0 = fmaf(h0[6], w1.z, acc0); acc0 = fmaf(h0[7], w1.w, acc0);
-        acc1 = fmaf(h1[0], w2.x, acc1); acc1 = fmaf(h1[1], w2.y, acc1); acc1 = fmaf(h1[2], w2.z, acc1); acc1 = fmaf(h1[3], w2.w, acc1);
-        acc1 = fmaf(h1[4], w3.x, acc1); acc1 = fmaf(h1[5], w3.y, acc1); acc1 = fmaf(h1[6], w3.z, acc1); acc1 = fmaf(h1[7], w3.w, acc1);
-    }
-    float acc = acc0 + acc1;
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) part[tg][img] = acc;
-    __syncthreads();
-    if (threadIdx.x < kDrtImgs) {
-        const int64_t n2 = (int64_t)(blockIdx.x / (13 * HD)) * kDrtImgs + threadIdx.x;
-        if (n2 < n_images) {
-            const int set2 = (w_row_base ? w_row_base[n2] / kE : 0) + hd;
-            drt_pre[(n2 * HD + hd) * 48 + o] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) +
-                                                (part[2][threadIdx.x] + part[3][threadIdx.x])) + bd_eff[set2 * 4 + variant];
+        const int64_t base = ((n * kH + yy) * kW + xx) * (int64_t)kE + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float hv[8];
+            load_h8(h_hi, h_lo, base + 256 * j, hv);
+            const float4 *wq = reinterpret_cast<const float4 *>(wv + tap * kE + lane * 8 + 256 * j);
+            const float4 w0 = wq[0], w1 = wq[1];
+            acc = fmaf(hv[0], w0.x, acc); acc = fmaf(hv[1], w0.y, acc);
+            acc = fmaf(hv[2], w0.z, acc); acc = fmaf(hv[3], w0.w, acc);
+            acc = fmaf(hv[4], w1.x, acc); acc = fmaf(hv[5], w1.y, acc);
+            acc = fmaf(hv[6], w1.z, acc); acc = fmaf(hv[7], w1.w, acc);
         }
     }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) drt_pre[win] = ((part[0] + part[1]) + (part[2] + part[3])) + bd_eff[set * 4 + variant];
 }
 
 // duration pre-activation of the 35 interior windows from the head GEMM: Z[p][kDrtCol0 + tap] = h[p,:] . wd_eff[set][0][tap,:],
@@ -1279,8 +1268,8 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             head_gather_kernel<<<(unsigned)((N * HD * kHW + 255) / 256), 256, 0, s>>>(
                 ws.z23, HD * kHeadCols, w->b23_eff, io->d_w_row_base, HD, ws.y2, ws.y3, N * HD * kHW);
             SPB_LAUNCH_CHECK();
-            head_drt_kernel<<<(unsigned)((N + kDrtImgs - 1) / kDrtImgs * HD * 13), kDrtImgs * kDrtTapGroups * 32, 0, s>>>(
-                ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff, io->d_w_row_base, HD, N, ws.drt_pre);
+            head_drt_kernel<<<(unsigned)(N * HD * 13), 128, 0, s>>>(ws.h_hi[nxt], ws.h_lo[nxt], w->wd_eff, w->bd_eff,
+                                                                   io->d_w_row_base, HD, ws.drt_pre);
             SPB_LAUNCH_CHECK();
             head_drt_gather_kernel<<<(unsigned)((N * HD * 35 * 32 + 255) / 256), 256, 0, s>>>(
                 ws.z23, HD * kHeadCols, w->bd_eff, io->d_w_row_base, HD, ws.drt_pre, N * HD * 35);

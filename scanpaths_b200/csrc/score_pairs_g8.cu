@@ -23,10 +23,24 @@ namespace spb {
 constexpr int kG = 8;                     // lanes per pair
 constexpr int kPairsPerWarp = 32 / kG;
 constexpr int kG8Warps = 4;               // warps per block -> 16 pairs per block
-constexpr int kWdC = 16;                  // with-duration columns per lane, at most (the warp uses ceil(m / 8))
+constexpr int kWdC = 16;                  // with-duration columns per lane, at most (the warp uses ceil(m / 8), rounded up to 4/8/12/16)
 constexpr int kWdPanel = kG * kWdC;       // 128
 
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// max(a, b) for finite doubles of which at most one is negative (every F value of the gap-0 recurrence is >= 0,
+// only F[i-1][j-1] + s can dip below): IEEE order equals the order of the bit patterns as signed 64-bit integers,
+// so the maximum is two integer compares and two selects on the ALU pipe instead of an FP64-pipe DSETP plus
+// selects plus a NaN fix-up.  Exact: it returns one of its operands.
+__device__ __forceinline__ double max_f64_bits(double a, double b) {
+    const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    return __longlong_as_double(ia > ib ? ia : ib);
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 
 // One panel of the gap-0 Needleman-Wunsch recurrence for the group's pair; returns F[n][col0 + pcols]
 // (group-uniform).  `active` false: the group idles through the warp's steps.
@@ -61,6 +75,7 @@ __device__ __forceinline__ double nw_panel_g8(const uint8_t *ar, const uint8_t *
     for (int c = 0; c < C; ++c) prev[c] = 0.0;
     double leftPrev = 0.0, myLast = 0.0;
     int ri = 0, rem = (UNIT || n == 0) ? 1 : arun[0];
+#pragma unroll 1
     for (int t = 0; t < steps_w; ++t) {
         const double recv = __shfl_up_sync(0xffffffffu, myLast, 1, kG);
         const int i = t - gl;
@@ -72,7 +87,7 @@ __device__ __forceinline__ double nw_panel_g8(const uint8_t *ar, const uint8_t *
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const double s = subd[abs(arow - brow[c]) * xbin + abs(acol - bcol[c])];
-                const double v = fmax(d + s, fmax(l, prev[c]));     // match | F[i][j-1] | F[i-1][j]  (gap 0)
+                const double v = max_f64_bits(d + s, max_f64_bits(l, prev[c]));   // match | F[i][j-1] | F[i-1][j]  (gap 0)
                 d = prev[c];
                 prev[c] = v;
                 l = v;
@@ -98,74 +113,79 @@ __device__ __forceinline__ double nw_panel_g8(const uint8_t *ar, const uint8_t *
 //   * the substitution score of a cell depends only on (human run, simulated run): a per-pair table
 //     S[u][v] in shared memory (it aliases the STDE tile W, which is initialised later) turns the lookup
 //     into one LDS at (row base + a per-column constant);
-//   * every lane owns `cw` consecutive columns, cw = ceil(longest string of the warp's four pairs / 8) <= 16
-//     (warp-uniform: the unrolled strip skips the cells >= cw with a uniform branch), so a 50-symbol string
-//     costs 7 cells per step and an 80-symbol one 10 -- not two 64-column panels;
+//   * every lane owns CW consecutive columns, CW = ceil(longest string of the warp's four pairs / 8) rounded up
+//     to 4, 8, 12 or 16 -- a compile-time strip (four instantiations behind a warp-uniform switch: straight-line
+//     code the scheduler can interleave, yet small enough for the instruction cache -- eight instantiations
+//     made the kernel 145 KB and 60 % of its stalls instruction fetches): a 50-symbol string costs 8 cells per
+//     step and an 80-symbol one 12 -- not two 64-column panels;
 //   * the recurrence is evaluated in two phases: t = F[i-1][j-1] + s and m = max(t, F[i-1][j]) only read the
 //     previous row (independent across the strip), then v = max(m, F[i][j-1]) is a running maximum -- the same
 //     three operands per cell as scanmatch.py:146-148, bit-identical, with a dependent chain of one max per cell;
 //   * the run counter advances branch-free.
-__device__ __forceinline__ double nw_wd_g8(const double *S, int spitch, const int *arun, int n, const int *brun,
-                                           int nb_runs, int col0, int pcols, int cw, bool active, bool more_panels,
-                                           double *bnd, int gl) {
-    const int nl = active ? (pcols + cw - 1) / cw : 0;        // lanes of the group that own columns
-    const int j0 = col0 + gl * cw;
-    int voff[kWdC];                                           // simulated run of each of my columns
+template <int CW>
+__device__ __noinline__ double nw_wd_g8(const double *S, int spitch, const int *arun, int n, const int *brun,
+                                        int nb_runs, int col0, int pcols, bool active, bool more_panels,
+                                        double *bnd, int gl) {
+    const int nl = active ? (pcols + CW - 1) / CW : 0;        // lanes of the group that own columns
+    const int j0 = col0 + gl * CW;
+    uint32_t voff[CW];                                        // byte offset of each of my columns' run in a row of S
     {
-        int acc = 0, r = 0;
+        int acc = 0, r = 0;                                   // run r covers columns [acc, acc + brun[r])
+        if (gl < nl)
+            while (r < nb_runs - 1 && acc + brun[r] <= j0) { acc += brun[r]; ++r; }
+        int end = (gl < nl) ? acc + brun[r] : 0;
 #pragma unroll
-        for (int c = 0; c < kWdC; ++c) {
-            voff[c] = 0;
-            if (c < cw && gl < nl) {
-                const int j = min(j0 + c, col0 + pcols - 1);  // columns past the end repeat the last symbol
-                while (r < nb_runs - 1 && acc + brun[r] <= j) { acc += brun[r]; ++r; }
-                voff[c] = r;
-            }
+        for (int c = 0; c < CW; ++c) {
+            // runs are >= 1 symbol long (empty ones were compacted out): at most one step per column;
+            // columns past the end of the string stay on the last run
+            if (gl < nl && j0 + c >= end && r < nb_runs - 1) { ++r; end += brun[r]; }
+            voff[c] = (uint32_t)r * 8u;
         }
     }
     const int steps_w = warp_max(nl > 0 ? n + nl - 1 : 0);
-    double prev[kWdC];
+    double prev[CW];
 #pragma unroll
-    for (int c = 0; c < kWdC; ++c) prev[c] = 0.0;
+    for (int c = 0; c < CW; ++c) prev[c] = 0.0;
     double leftPrev = 0.0, myLast = 0.0;
     int ri = 0, rem = n == 0 ? 1 : arun[0];
+    uint32_t row = (uint32_t)__cvta_generic_to_shared(S);     // shared-space address of S[human run ri][0]
+    const uint32_t row_step = (uint32_t)spitch * 8u;
+#pragma unroll 1
     for (int t = 0; t < steps_w; ++t) {
         const double recv = __shfl_up_sync(0xffffffffu, myLast, 1, kG);
         const int i = t - gl;
         if (i >= 0 && i < n && gl < nl) {
             const double leftCur = (gl == 0) ? (col0 == 0 ? 0.0 : bnd[i + 1]) : recv;
-            const double *Sr = S + ri * spitch;
-            double mm[kWdC];
+            double mm[CW];
             double d = leftPrev;
 #pragma unroll
-            for (int c = 0; c < kWdC; ++c)
-                if (c < cw) {                                               // warp-uniform
-                    const double tt = d + Sr[voff[c]];                      // F[i-1][j-1] + s
-                    d = prev[c];
-                    mm[c] = fmax(tt, d);                                    // | F[i-1][j]
-                }
+            for (int c = 0; c < CW; ++c) {
+                const double tt = d + lds_f64(row + voff[c]);               // F[i-1][j-1] + s
+                d = prev[c];
+                mm[c] = max_f64_bits(tt, d);                                // | F[i-1][j]
+            }
             double l = leftCur;
 #pragma unroll
-            for (int c = 0; c < kWdC; ++c)
-                if (c < cw) {
-                    l = fmax(mm[c], l);                                     // | F[i][j-1]
-                    prev[c] = l;
-                }
+            for (int c = 0; c < CW; ++c) {
+                l = max_f64_bits(mm[c], l);                                 // | F[i][j-1]
+                prev[c] = l;
+            }
             leftPrev = leftCur;
             myLast = l;
             if (more_panels && gl == kG - 1) bnd[i + 1] = l;                // a full panel: its last column feeds the next one
             --rem;                                                          // next row: advance the human run, branch-free
-            const int adv = rem == 0 ? 1 : 0;
-            ri += adv;
+            const bool adv = rem == 0;
+            ri += adv ? 1 : 0;
+            row += adv ? row_step : 0u;
             const int nxt = arun[min(ri, n - 1)];                           // (runs <= symbols: always inside the slice)
             rem = adv ? ((i + 1 < n) ? nxt : 1) : rem;
         }
     }
     // F[n][col0 + pcols]: strip position of the last column in the last lane that owns columns
     double res = 0.0;
-    const int cm = nl > 0 ? (pcols - 1) - (nl - 1) * cw : 0;
+    const int cm = nl > 0 ? (pcols - 1) - (nl - 1) * CW : 0;
 #pragma unroll
-    for (int c = 0; c < kWdC; ++c)
+    for (int c = 0; c < CW; ++c)
         if (c == cm) res = prev[c];
     return __shfl_sync(0xffffffffu, res, nl > 0 ? nl - 1 : 0, kG);
 }
@@ -184,6 +204,7 @@ __device__ __forceinline__ int lev_g8(const int *a, int n, const int *b, int m, 
     }
     int leftPrev = j0, myLast = 0;
     const int steps_w = warp_max(nl > 0 ? n + nl - 1 : 0);
+#pragma unroll 1
     for (int t = 0; t < steps_w; ++t) {
         const int recv = __shfl_up_sync(0xffffffffu, myLast, 1, kG);
         const int i = t - gl;
@@ -229,17 +250,20 @@ __device__ __forceinline__ double stde_g8(const double *ax, const double *ay, in
     __syncwarp();
     const int kmax_w = warp_max(kmax);
     double total = 0.0;
+#pragma unroll 1
     for (int k = 1; k <= kmax_w; ++k) {
         const bool kon = k <= kmax;
         const int nw = kon ? Ls - k + 1 : 0, nh = kon ? Lh - k + 1 : 0;
         const int nw_w = warp_max(nw), nh_w = warp_max(nh);
         double acc = 0.0;
+#pragma unroll 1
         for (int i0 = 0; i0 < nw_w; i0 += kG) {
             const int i = i0 + gl;
             const bool on = i < nw;
             double best = INFINITY;
             const double *dp = D + (on ? (i + k - 1) * pitch + (k - 1) : 0);
             double *wp = W + (on ? i * pitch : 0);
+#pragma unroll 2
             for (int j = 0; j < nh_w; ++j) {
                 if (on && j < nh) {
                     const double w = wp[j] + dp[j];
@@ -375,11 +399,18 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
             const int npan = act ? (m_wd + kWdPanel - 1) / kWdPanel : 0;
             const int npan_w = warp_max(npan);
             double corner = 0.0;
+#pragma unroll 1
             for (int pn = 0; pn < npan_w; ++pn) {
                 const bool on = pn < npan;
                 const int col0 = pn * kWdPanel;
                 const int pcols = on ? min(kWdPanel, m_wd - col0) : 0;
-                const double c = nw_wd_g8(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, cw, on, pn + 1 < npan, bnd, gl);
+                double c;
+                switch ((cw + 3) >> 2) {                               // strip width rounded up to 4, 8, 12, 16
+                case 1: c = nw_wd_g8<4>(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, on, pn + 1 < npan, bnd, gl); break;
+                case 2: c = nw_wd_g8<8>(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, on, pn + 1 < npan, bnd, gl); break;
+                case 3: c = nw_wd_g8<12>(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, on, pn + 1 < npan, bnd, gl); break;
+                default: c = nw_wd_g8<16>(S, spitch, arun, n_wd, brun, nb_runs, col0, pcols, on, pn + 1 < npan, bnd, gl); break;
+                }
                 if (on) corner = c;
                 __syncwarp();
             }

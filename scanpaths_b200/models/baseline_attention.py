@@ -261,6 +261,7 @@ class CudaDecoder:
         self.tensors, self.w = prepare_weights(state_dict, task, self.device)
         self.heads = int(self.w.n_heads)
         self._ws, self._ws_n = None, 0
+        self._graphs = {}
 
     def _workspace(self, n):
         if self._ws is None or self._ws_n < n:
@@ -307,6 +308,44 @@ class CudaDecoder:
             if not dense:
                 probs[:, n0:n1], mu[:, n0:n1], s2[:, n0:n1], amap[:, n0:n1] = p_w, m_w, s_w, a_w
         return probs, mu, s2, amap.view(HD, N, T, 30, 40)
+
+
+def _decode_graphed(self, visual_feature, attention_maps=None, tasks=None):
+    """decode() replayed from a CUDA graph: the ~230 launches of a 16-step rollout (each with its tensor-map
+    encodes) become one cudaGraphLaunch -- what matters when the wave is small and the rollout is launch-bound
+    (the SCST step: 4 images).  Inputs are copied into static buffers; the returned tensors are the graph's
+    static outputs and are overwritten by the next call with the same shape."""
+    vf = visual_feature.detach().to(self.device, torch.float32)
+    N = vf.shape[0]
+    assert N <= self.wave, "graphed decode handles one wave"
+    key = (N, attention_maps is not None and self.task != "OSIE", tasks is not None)
+    g = self._graphs.get(key)
+    if g is None:
+        st = {"vf": torch.empty_like(vf).contiguous(),
+              "att": torch.empty((N, 1, 30, 40), dtype=torch.float32, device=self.device) if key[1] else None,
+              "tasks": torch.empty((N,), dtype=torch.int64, device=self.device) if key[2] else None}
+        st["vf"].copy_(vf)
+        if key[1]:
+            st["att"].copy_(attention_maps.reshape(N, 1, 30, 40))
+        if key[2]:
+            st["tasks"].copy_(torch.as_tensor(tasks).to(self.device))
+        self.decode(st["vf"], st["att"], st["tasks"])                     # warm-up: workspace, attributes, modules
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["out"] = self.decode(st["vf"], st["att"], st["tasks"])
+        g = self._graphs[key] = (graph, st)
+    graph, st = g
+    st["vf"].copy_(vf, non_blocking=True)
+    if key[1]:
+        st["att"].copy_(attention_maps.reshape(N, 1, 30, 40), non_blocking=True)
+    if key[2]:
+        st["tasks"].copy_(torch.as_tensor(tasks).to(self.device), non_blocking=True)
+    graph.replay()
+    return st["out"]
+
+
+CudaDecoder.decode_graphed = _decode_graphed
 
 
 def _result_dict(task, probs, mu, s2, amap):

@@ -190,7 +190,7 @@ def score_pairs(human: PathPack, sim: PathPack, pair_h: torch.Tensor, pair_s: to
     if out is None:
         out = torch.empty((P, 4), dtype=torch.float64, device=dev)
     err = torch.zeros((1,), dtype=torch.int32, device=dev)
-    if workspace is None and P > 0 and sim.n > 0 and int(sim.nwd.max().item()) > 64:    # longer than one panel
+    if workspace is None and P > 0 and sim.n > 0 and int(sim.nwd.max().item()) > 128:   # longer than one panel
         workspace = Workspace(int(human.nwd.max().item()), dev)
     hp, sp = human.c_struct(), sim.c_struct()
     with torch.cuda.device(dev):

@@ -152,6 +152,44 @@ def human_evaluation(dataloader, per_image_best=False):
     return m, s, {name: sc_ for name, sc_ in zip(names, per)}
 
 
+def human_evaluation_packed(xyd, lens, n_subjects=None, per_image_best=False, img_names=None):
+    """human_evaluation on the packed layout (scanpaths_b200.dataset / scoring.pack_subject_lists):
+    xyd [N,S,Lmax,3] f64 (seconds), lens [N,S] i32, n_subjects [N] or None (= S everywhere).  Same pair
+    order, same aggregates and the same return value as ``human_evaluation`` -- without building Python lists
+    of structured arrays or a Python-level pair loop (the pair map is one vectorised numpy expression)."""
+    cfg = _eval_cfg()
+    dev = cfg.device
+    xyd = torch.as_tensor(xyd, dtype=torch.float64)
+    lens = torch.as_tensor(lens, dtype=torch.int32)
+    N, Smax, L, _ = xyd.shape
+    nsub = np.full(N, Smax, dtype=np.int64) if n_subjects is None else np.asarray(torch.as_tensor(n_subjects).cpu(), dtype=np.int64)
+    i, j = np.nonzero(~np.eye(Smax, dtype=bool))                    # ordered pairs (i, j != i), i-major like :30-33
+    keep = (i[None, :] < nsub[:, None]) & (j[None, :] < nsub[:, None])
+    base = (np.arange(N, dtype=np.int64) * Smax)[:, None]
+    pair_h = (base + i[None, :])[keep].astype(np.int32)
+    pair_s = (base + j[None, :])[keep].astype(np.int32)
+    sizes = nsub * (nsub - 1)
+    pack = S.prep_paths(xyd.reshape(N * Smax, L, 3).to(dev), lens.reshape(-1).to(dev), cfg)
+    scores = S.score_pairs(pack, pack, torch.from_numpy(pair_h).to(dev), torch.from_numpy(pair_s).to(dev), cfg)
+    if per_image_best or not np.all(nsub == nsub[-1]):
+        sc = scores.cpu().numpy()
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        sed_b = np.array([sc[off[k]:off[k + 1], 2].min() for k in range(N) if sizes[k]])
+        stde_b = np.array([sc[off[k]:off[k + 1], 3].max() for k in range(N) if sizes[k]])
+        m = {"MultiMatch": _nan5(),
+             "ScanMatch": {"w/o duration": sc[:, 1].mean(), "with duration": sc[:, 0].mean()},
+             "VAME": {"SED": sc[:, 2].mean(), "STDE": sc[:, 3].mean(), "SED_best": sed_b.mean(),
+                      "STDE_best": stde_b.mean()}}
+        s = {"MultiMatch": _nan5(),
+             "ScanMatch": {"w/o duration": sc[:, 1].std(), "with duration": sc[:, 0].std()},
+             "VAME": {"SED": sc[:, 2].std(), "STDE": sc[:, 3].std(), "SED_best": sed_b.std(), "STDE_best": stde_b.std()}}
+    else:
+        m, s = _metric_dicts(scores, int(nsub[-1]) - 1)
+    per = _per_group_means(scores, sizes)
+    names = img_names if img_names is not None else list(range(N))
+    return m, s, {name: sc_ for name, sc_ in zip(names, per)}
+
+
 def pairs_eval(gt_fix_vectors, predict_fix_vectors, ScanMatchwithDuration=None, ScanMatchwithoutDuration=None,
                is_eliminating_nan=True):
     """OSIE/utils/evaluation.py:284-340 -> [N, 11] (float32 values).  The two ScanMatch

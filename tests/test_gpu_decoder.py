@@ -287,3 +287,21 @@ def test_decode_full_wave_is_independent_of_batch_layout(lib):
     # and a partial wave (pad rows of the GEMM row blocks) equals the head of the full one
     p2, m2, s2, a2 = dec.decode(vf[:37].contiguous())
     assert torch.equal(p2, p0[:, :37]) and torch.equal(m2, m0[:, :37])
+
+
+def test_decode_graph_replay_equals_eager(lib):
+    """decode_graphed(): the rollout captured once in a CUDA graph and replayed on new inputs is bit-identical to
+    the eager launches (AiR: attention maps, two streams, two heads)."""
+    from scanpaths_b200.models.baseline_attention import CudaDecoder
+    from scanpaths_b200.weights import random_state_dict, synthetic_features
+    dev = torch.device("cuda")
+    sd = random_state_dict("AiR", 3, calibrated=True, bias_std=0.05)
+    dec = CudaDecoder(sd, "AiR", 5, dev, wave=4)
+    for seed in (1, 2, 3):
+        vf, att = synthetic_features(4, seed, attention=True)
+        eager = [t.clone() for t in dec.decode(vf.to(dev), att.to(dev))]
+        graphed = dec.decode_graphed(vf.to(dev), att.to(dev))
+        torch.cuda.synchronize()
+        for a, b in zip(eager, graphed):
+            assert torch.equal(a, b)
+    assert len(dec._graphs) == 1

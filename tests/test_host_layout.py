@@ -62,3 +62,45 @@ def test_predictions_to_records_match_test_py(golden_dir):
         assert r["X"] == e["X"] and r["Y"] == e["Y"] and r["T"] == e["T"]
     import json
     json.dumps(recs)                                                 # test.py:151 dumps them as JSON
+
+
+def test_dataset_mirror_matches_reference_dataset(golden_dir, tmp_path):
+    """scanpaths_b200.dataset against the reference's OSIE_evaluation.__getitem__ / collate_func output recorded
+    in tests/golden/dataset_osie.npz (same JSON records in, bit-equal f8 rows out), the packed layout built from
+    it, and the JSON writer of test.py:151-152."""
+    import json
+    from scanpaths_b200 import dataset as D
+    g = np.load(os.path.join(golden_dir, "dataset_osie.npz"))
+    records = json.loads(str(g["records_json"]))
+    groups = D.group_fixations_by_image(records)
+    assert list(groups) == [str(n) for n in g["img_names"]]
+    lists = []
+    for i, (name, idx) in enumerate(groups.items()):
+        fvs = D.image_fix_vectors(records, idx)
+        assert len(fvs) == int(g["n_sub_%d" % i])
+        for j, fv in enumerate(fvs):
+            ref = g["fix_%d_%d" % (i, j)]
+            got = np.stack([fv["start_x"], fv["start_y"], fv["duration"]], 1).reshape(-1, 3)
+            np.testing.assert_array_equal(got, ref)                      # float32 division, stored as f8: bit-equal
+        lists.append(fvs)
+    # collate wrapper: reference dict + the packed layout
+    ref_collate = lambda batch: {"fix_vectors": [b["fix_vectors"] for b in batch], "img_names": [b["img_name"] for b in batch]}
+    coll = D.PackedCollate(ref_collate, pin=False)
+    b1 = coll([{"fix_vectors": lists[0], "img_name": "a"}, {"fix_vectors": lists[1], "img_name": "b"}])
+    b2 = coll([{"fix_vectors": lists[2], "img_name": "c"}])
+    xyd, lens, nsub = D.concat_packed([b1["fix_packed"], b2["fix_packed"]])
+    assert nsub.tolist() == [3, 1, 4] and tuple(xyd.shape[:2]) == (3, 4)
+    for i in range(3):
+        for j in range(int(nsub[i])):
+            ref = g["fix_%d_%d" % (i, j)]
+            assert int(lens[i, j]) == len(ref)
+            np.testing.assert_array_equal(xyd[i, j, :len(ref)].numpy(), ref)
+        assert (lens[i, int(nsub[i]):] == 0).all()
+    # prediction writer
+    sampled = {"xyd": torch.tensor([[[4.0, 12.0, 0.25], [36.0, 20.0, 0.5]], [[100.0, 60.0, 0.125], [0, 0, 0]]], dtype=torch.float64),
+               "len": torch.tensor([2, 1], dtype=torch.int32)}
+    path = tmp_path / "predicts.json"
+    D.write_prediction_records(str(path), sampled, ["x.jpg"], 1)
+    back = json.load(open(path))
+    assert back == [{"name": "x.jpg", "repeat_id": 1, "X": [4.0, 36.0], "Y": [12.0, 20.0], "T": [250.0, 500.0], "length": 2},
+                    {"name": "x.jpg", "repeat_id": 2, "X": [100.0], "Y": [60.0], "T": [125.0], "length": 1}]
