@@ -349,9 +349,11 @@ def profile_pass(lib, w, steps=1):
     from scanpaths_b200 import _lib
     cap = 200 * (w.N // w.args.wave + 1) * steps * max(1, w.heads)
     _lib.check(lib.spb_profile_enable(cap), "spb_profile_enable")
+    overlap, w.pipe.overlap_tail = w.pipe.overlap_tail, False      # one stream: every bracket times its kernels alone
     for _ in range(steps):
         w.step()
     torch.cuda.synchronize()
+    w.pipe.overlap_tail = overlap
     ms_buf = np.zeros(cap, dtype=np.float32); tag_buf = np.zeros(cap, dtype=np.int32)
     n_out = C.c_int32(0)
     _lib.check(lib.spb_profile_collect(_lib.ptr(ms_buf), _lib.ptr(tag_buf), cap, C.byref(n_out)), "spb_profile_collect")

@@ -20,7 +20,7 @@ MIN_LEN_VALID = 3    # multimatch_gaze's NaN rule, which pairs_eval's row elimin
 
 class ScanpathPipeline:
     def __init__(self, state_dict, task="OSIE", steps=16, k_samples=10, min_length=1, device="cuda", wave=256,
-                 seed=0, use_tensor_cores=True):
+                 seed=0, use_tensor_cores=True, overlap_tail=True):
         self.device = torch.device(device)
         self.task, self.K, self.steps, self.wave = task, int(k_samples), int(steps), int(wave)
         self.decoder = CudaDecoder(state_dict, task, steps, self.device, wave, use_tensor_cores)
@@ -32,6 +32,10 @@ class ScanpathPipeline:
         self._pairs = {}
         self._ws = None
         self._cs = None
+        # sampling + scoring + reduction of wave w run on a side stream while wave w+1 decodes: those kernels use
+        # neither tensor cores nor much bandwidth (latency / issue bound), so they fill the gaps of the decode
+        self.overlap_tail = bool(overlap_tail)
+        self._ts = None
 
     # ---- human scanpaths: packed once, resident on the device
     def set_humans(self, xyd, lens, n_subjects=None):
@@ -57,6 +61,11 @@ class ScanpathPipeline:
             self._cs = torch.cuda.Stream(device=self.device)
         return self._cs
 
+    def _tail_stream(self):
+        if self._ts is None:
+            self._ts = torch.cuda.Stream(device=self.device)
+        return self._ts
+
     def _pair_map(self, n, n0):
         key = (n, n0, self.n_subjects, self.K)
         if key not in self._pairs:
@@ -65,6 +74,41 @@ class ScanpathPipeline:
             if len(self._pairs) > 64:
                 self._pairs.pop(next(iter(self._pairs)))
         return self._pairs[key]
+
+    def _tail(self, hd, n0, n1, N, probs, mu, s2, ph, ps, cnt, valid_min_len, table, reward, gvalid, scores_all, acc,
+              paths, paths_host, stream, copy_stream):
+        """sample -> prep -> score -> reduce for one head of one wave, on the current stream."""
+        K, Sn, T, n = self.K, self.n_subjects, self.steps, n1 - n0
+        full = n == N
+        smp = self.sampler.sample_paths(probs, mu, s2, K)
+        pp = S.prep_paths(smp["xyd"], smp["len"], self.cfg)
+        sc = scores_all[hd].view(-1, 4) if (scores_all is not None and full) else None
+        sc = S.score_pairs(self.humans, pp, ph, ps, self.cfg, workspace=self._ws, check=False, out=sc)
+        # the reduced tables of a wave are dense [K, n, ...] blocks; written in place when one wave covers the
+        # batch, else copied into the [K, N, ...] results
+        tab_w = table[hd].view(K * N, 11) if full else None
+        rew_w = reward[hd].view(K * N) if full else None
+        gv_w = gvalid[hd].view(K * N) if full else None
+        tab_w, rew_w, gv_w = S.reduce_pairs(sc, Sn, n_images=n, group_count=cnt, pair_h=ph, pair_s=ps,
+                                            len_h=self.humans.len, len_s=pp.len, min_len_valid=valid_min_len,
+                                            acc=acc, out=tab_w, reward=rew_w, group_valid=gv_w)
+        if not full:
+            table[hd, :, n0:n1] = tab_w.view(K, n, 11)
+            reward[hd, :, n0:n1] = rew_w.view(K, n)
+            gvalid[hd, :, n0:n1] = gv_w.view(K, n)
+            if scores_all is not None:
+                scores_all[hd, :, n0:n1] = sc.view(K, n, Sn, 4)
+        if paths is not None:
+            paths.append((hd, n0, n1, smp))
+        if paths_host is not None:
+            done = torch.cuda.Event()
+            done.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                paths_host[0][hd, :, n0:n1].copy_(smp["xyd"].view(K, n, T, 3), non_blocking=True)
+                paths_host[1][hd, :, n0:n1].copy_(smp["len"].view(K, n), non_blocking=True)
+            smp["xyd"].record_stream(copy_stream)
+            smp["len"].record_stream(copy_stream)
 
     def run(self, visual_feature, attention_maps=None, tasks=None, keep_scores=False, valid_min_len=MIN_LEN_VALID,
             keep_paths=False, paths_host=None):
@@ -92,6 +136,7 @@ class ScanpathPipeline:
         main = torch.cuda.current_stream(dev)
         starts = list(range(0, N, self.wave))
         full = len(starts) == 1
+        tail = self._tail_stream() if (self.overlap_tail and not full) else main
 
         def fetch(n0):
             n1 = min(N, n0 + self.wave)
@@ -117,37 +162,18 @@ class ScanpathPipeline:
             probs, mu, s2, _ = self.decoder.decode(vf, att, tk)
             ph, ps = self._pair_map(n, n0)
             cnt = None if self.subject_count is None else self.subject_count[n0:n1]
-            for hd in range(HD):
-                smp = self.sampler.sample_paths(probs[hd], mu[hd], s2[hd], K)
-                pp = S.prep_paths(smp["xyd"], smp["len"], self.cfg)
-                sc = scores_all[hd] if (keep_scores and full) else None
-                sc = S.score_pairs(self.humans, pp, ph, ps, self.cfg, workspace=self._ws, check=False,
-                                   out=None if sc is None else sc.view(-1, 4))
-                # the reduced tables of a wave are dense [K, n, ...] blocks; written in place when one wave
-                # covers the batch, else copied into the [K, N, ...] results
-                tab_w = table[hd].view(K * N, 11) if full else None
-                rew_w = reward[hd].view(K * N) if full else None
-                gv_w = gvalid[hd].view(K * N) if full else None
-                tab_w, rew_w, gv_w = S.reduce_pairs(sc, Sn, n_images=n, group_count=cnt, pair_h=ph, pair_s=ps,
-                                                    len_h=self.humans.len, len_s=pp.len, min_len_valid=valid_min_len,
-                                                    acc=accs[hd], out=tab_w, reward=rew_w, group_valid=gv_w)
-                if not full:
-                    table[hd, :, n0:n1] = tab_w.view(K, n, 11)
-                    reward[hd, :, n0:n1] = rew_w.view(K, n)
-                    gvalid[hd, :, n0:n1] = gv_w.view(K, n)
-                    if keep_scores:
-                        scores_all[hd, :, n0:n1] = sc.view(K, n, Sn, 4)
-                if keep_paths:
-                    paths.append((hd, n0, n1, smp))
-                if paths_host is not None:
-                    done = torch.cuda.Event()
-                    done.record(main)
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(done)
-                        paths_host[0][hd, :, n0:n1].copy_(smp["xyd"].view(K, n, T, 3), non_blocking=True)
-                        paths_host[1][hd, :, n0:n1].copy_(smp["len"].view(K, n), non_blocking=True)
-                    smp["xyd"].record_stream(copy_stream)
-                    smp["len"].record_stream(copy_stream)
+            if tail is not main:
+                decoded = torch.cuda.Event()
+                decoded.record(main)
+                tail.wait_event(decoded)
+                for t_ in (probs, mu, s2):
+                    t_.record_stream(tail)
+            with torch.cuda.stream(tail):
+                for hd in range(HD):
+                    self._tail(hd, n0, n1, N, probs[hd], mu[hd], s2[hd], ph, ps, cnt, valid_min_len, table, reward,
+                               gvalid, scores_all, accs[hd], paths, paths_host, tail, copy_stream)
+        if tail is not main:
+            main.wait_stream(tail)
         if paths_host is not None:
             main.wait_stream(copy_stream)
         acc = torch.stack([a[:16] for a in accs], 0)
