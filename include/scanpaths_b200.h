@@ -176,6 +176,8 @@ typedef struct spb_reduce_args {
     int64_t n_groups;
     int32_t group_size, n_images, min_len_valid;
     int32_t acc_blocks;            /* set by the library */
+    int32_t mean_over_kept;        /* 0: table means divide by the subject count (pairs_eval, :329); 1: by the number of */
+    int32_t reserved;              /*    surviving rows (AiR pairs_eval_scanmatch_performance_related, evaluation.py:405-416) */
 } spb_reduce_args;
 
 int64_t spb_reduce_acc_bytes(void);

@@ -34,7 +34,8 @@ class ReduceArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_scores", "d_valid", "d_pair_h", "d_pair_s", "d_len_h", "d_len_s",
                                           "d_group_count", "d_out", "d_reward", "d_group_valid", "d_acc")] + \
                [("acc_bytes", C.c_int64), ("n_groups", C.c_int64), ("group_size", C.c_int32), ("n_images", C.c_int32),
-                ("min_len_valid", C.c_int32), ("acc_blocks", C.c_int32)]
+                ("min_len_valid", C.c_int32), ("acc_blocks", C.c_int32), ("mean_over_kept", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class PathPack(C.Structure):

@@ -383,6 +383,7 @@ reduce_pairs_kernel(spb_reduce_args a) {
             loc[13] += 1.0;
         }
         const float qnan = __int_as_float(0x7fc00000);
+        const int div = a.mean_over_kept ? kept : cnt;
         double rw = nan("");
         if (a.d_out) {
             float *o = a.d_out + 11 * g;
@@ -391,8 +392,8 @@ reduce_pairs_kernel(spb_reduce_args a) {
                 // reference's `np.any(np.isnan(metrics_reward))` trial rejection (train.py:237) sees NaN exactly
                 // where the reference does -- when no row of the image survives
                 o[0] = o[1] = o[2] = o[3] = o[4] = 0.0f;
-                o[5] = (float)(s_wod / cnt); o[6] = (float)(s_wd / cnt);
-                o[7] = (float)(s_sed / cnt); o[8] = (float)(s_stde / cnt);
+                o[5] = (float)(s_wod / div); o[6] = (float)(s_wd / div);
+                o[7] = (float)(s_sed / div); o[8] = (float)(s_stde / div);
                 o[9] = (float)best_sed; o[10] = (float)best_stde;
             } else {
                 for (int i = 0; i < 11; ++i) o[i] = qnan;
@@ -400,7 +401,7 @@ reduce_pairs_kernel(spb_reduce_args a) {
         }
         if (kept > 0) {
             // the reward is computed from the float32 table (train.py:241,252: scipy.stats.hmean of slots 5, 6)
-            const double x = (double)(float)(s_wod / cnt), y = (double)(float)(s_wd / cnt);
+            const double x = (double)(float)(s_wod / div), y = (double)(float)(s_wd / div);
             rw = (x > 0.0 && y > 0.0) ? 2.0 / (1.0 / x + 1.0 / y) : 0.0;
             loc[14] += 1.0;
         }

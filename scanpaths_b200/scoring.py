@@ -233,7 +233,8 @@ def reduce_pairs(scores: torch.Tensor, group_size: int, *, n_images: int = 0, gr
                  pair_h: torch.Tensor | None = None, pair_s: torch.Tensor | None = None,
                  len_h: torch.Tensor | None = None, len_s: torch.Tensor | None = None, min_len_valid: int = 0,
                  valid: torch.Tensor | None = None, acc: torch.Tensor | None = None, out: torch.Tensor | None = None,
-                 reward: torch.Tensor | None = None, group_valid: torch.Tensor | None = None):
+                 reward: torch.Tensor | None = None, group_valid: torch.Tensor | None = None,
+                 mean_over_kept: bool = False):
     """a7 in one pass (spb_reduce_pairs): table [G,11] f32, reward [G] f64, group_valid [G] u8, and the running
     sums of `evaluation` added into `acc` (new_accumulator).  Padded subjects (index >= group_count[image]) are
     skipped; with min_len_valid the MultiMatch NaN rule is evaluated on the device from the path lengths."""
@@ -255,6 +256,7 @@ def reduce_pairs(scores: torch.Tensor, group_size: int, *, n_images: int = 0, gr
     a.d_out, a.d_reward, a.d_group_valid = out.data_ptr(), reward.data_ptr(), group_valid.data_ptr()
     a.d_acc, a.acc_bytes = p(acc), (acc.numel() * 8 if acc is not None else 0)
     a.n_groups, a.group_size, a.n_images, a.min_len_valid = G, int(group_size), int(n_images), int(min_len_valid)
+    a.mean_over_kept = 1 if mean_over_kept else 0
     with torch.cuda.device(dev):
         _lib.check(lib.spb_reduce_pairs(C.byref(a), _lib.current_stream()), "spb_reduce_pairs")
     return out, reward, group_valid

@@ -157,3 +157,88 @@ class ScstRewardStep:
                 return loss, aux
         raise _lib.SpbError("SCST: fewer than %d accepted trials after %d rounds (every sampled scanpath shorter "
                             "than 3 fixations?)" % (self.K, self.max_rounds))
+
+
+class AirScstStep:
+    """The AiR SCST batch (AiR/train.py:219-342) on the device: for the correct-answer head (`good_*`, scored
+    against the subjects who answered correctly) and the incorrect-answer head (`poor_*`), K trials each:
+
+        same[k,n] = hmean over (SM w/o, SM with duration) of the mean over the subjects whose performance equals
+                    the head's, diff[k,n] likewise over the other subjects     (pairs_eval_scanmatch_performance_
+                    related, AiR/utils/evaluation.py:361-420; groups without a subject count 0, train.py:283-284)
+        loss      = sum over both heads of ScstLoss(reward = same, baseline = mean over the head's K trials)
+
+    That is the loss the reference ACTUALLY optimises: in AiR/train.py:330-338 the `+ args.lambda_5 * (...)`
+    lines are separate expression statements, so the Consistency-Divergence term never reaches `loss`.  With
+    `lambda_5 != 0` this class adds the term as it was evidently meant (through ScstLoss's `extra_adv`):
+        difference_reward = |(same - diff) - (gt_same - gt_diff)| * usable        (train.py:322-327)
+    with the human-vs-human scores of gtpairs_eval_scanmatch_performance_related (:227-229, :311-321)."""
+
+    def __init__(self, sampler, device, rl_sample_number=5, lambda_5=0.0):
+        self.sampler, self.device, self.K, self.lambda_5 = sampler, torch.device(device), int(rl_sample_number), float(lambda_5)
+        self.cfg = S.ScoreConfig.evaluation(device=self.device, dur_scale=1000.0)
+        self.humans = None
+
+    def set_humans(self, fix_vectors, performances):
+        xyd, lens, nsub = S.pack_subject_lists(fix_vectors)
+        N, Sn, L, _ = xyd.shape
+        self.N, self.Sn = N, Sn
+        self.humans = S.prep_paths(xyd.reshape(N * Sn, L, 3).to(self.device, non_blocking=True),
+                                   lens.reshape(N * Sn).to(self.device, non_blocking=True), self.cfg)
+        perf = torch.zeros((N, Sn), dtype=torch.bool)
+        real = torch.zeros((N, Sn), dtype=torch.bool)
+        for i, p in enumerate(performances):
+            for j, v in enumerate(p):
+                perf[i, j] = bool(v == True)        # noqa: E712 (the reference compares with ==)
+                real[i, j] = True
+        self.perf, self.real = perf.to(self.device), real.to(self.device)
+        self._ws = S.Workspace(int(self.humans.nwd.max().item()), self.device)
+        self._pairs = S.grid_pairs(N, self.K, Sn, self.device)
+        self.gt_scores = None
+        if self.lambda_5 != 0.0:
+            from .utils.evaluation import gtpairs_eval_scanmatch_performance_related
+            g, p, d = gtpairs_eval_scanmatch_performance_related(fix_vectors, None, None, performances)
+            hm = lambda a: _hmean2(torch.nan_to_num(torch.from_numpy(a).to(self.device)))
+            self.gt_scores = (hm(g), hm(p), hm(d))             # good-good, poor-poor, good-poor  [N]
+
+    def _head(self, probs, mu, s2, given):
+        K, N, Sn = self.K, self.N, self.Sn
+        with torch.no_grad():
+            smp = self.sampler.sample_paths(probs, mu, s2, K)
+            pp = S.prep_paths(smp["xyd"], smp["len"], self.cfg)
+            ph, ps = self._pairs
+            sc = S.score_pairs(self.humans, pp, ph, ps, self.cfg, workspace=self._ws, check=False)
+            same_m = (self.real & (self.perf == given)).to(torch.uint8)
+            diff_m = (self.real & (self.perf != given)).to(torch.uint8)
+            out = []
+            for m in (same_m, diff_m):
+                valid = m.unsqueeze(0).expand(K, N, Sn).contiguous().view(-1)
+                tab, rew, _ = S.reduce_pairs(sc, Sn, n_images=N, valid=valid, mean_over_kept=True)
+                out.append((tab.view(K, N, 11)[..., 5:7], torch.nan_to_num(rew.view(K, N))))   # NaN (empty group) -> 0
+        return smp, out[0], out[1]
+
+    def __call__(self, predict):
+        """predict: the AiR model's output dict (good_* / poor_* tensors).  Returns (loss, aux)."""
+        assert self.humans is not None, "set_humans() first"
+        total, aux = None, {}
+        for name, given in (("good", True), ("poor", False)):
+            probs, mu, s2 = (predict[name + "_all_actions_prob"], predict[name + "_log_normal_mu"],
+                             predict[name + "_log_normal_sigma2"])
+            smp, (same_tab, same), (diff_tab, diff) = self._head(probs, mu, s2, given)
+            extra = None
+            if self.lambda_5 != 0.0:
+                gt_same = self.gt_scores[0 if given else 1].unsqueeze(0)
+                gt_diff = self.gt_scores[2].unsqueeze(0)
+                usable = ((gt_same != 0) & (gt_diff != 0)).to(torch.float64)
+                dr = ((same - diff) - (gt_same - gt_diff)).abs() * usable
+                extra = (self.lambda_5 * (dr - dr.mean(0, keepdim=True))).float()
+            loss, a = scst_loss(probs, mu, s2, smp, same, None, self.K, extra)
+            total = loss if total is None else total + loss
+            aux[name] = dict(a, same=same, diff=diff, same_table=same_tab, diff_table=diff_tab, samples=smp)
+        return total, aux
+
+
+def _hmean2(t):
+    """scipy.stats.hmean over the last axis of [..., 2] non-negative values (0 if either is 0)."""
+    a, b = t[..., 0].double(), t[..., 1].double()
+    return torch.where((a > 0) & (b > 0), 2.0 / (1.0 / a + 1.0 / b), torch.zeros_like(a))

@@ -224,3 +224,57 @@ def test_train_loop_shape_with_mirror_api(data):
     loss.backward()
     assert torch.isfinite(loss) and torch.isfinite(probs.grad).all() and (probs.grad != 0).any()
     assert torch.isfinite(mu.grad).all() and torch.isfinite(s2.grad).all()
+
+
+def test_air_scst_step_matches_oracle(data):
+    """AiR's SCST batch: same / diff rewards of both heads equal the oracle's
+    pairs_eval_scanmatch_performance_related on the very same samples, and the loss equals the reference's
+    effective expression (AiR/train.py:286-340: the lambda_5 lines are no-op statements) evaluated by the
+    SCST oracle per head."""
+    from oracle import scoring as O
+    from oracle import scst as OS
+    from golden.make_goldens import to_struct
+    from scanpaths_b200.models.sampling import Sampling
+    from scanpaths_b200.scst import AirScstStep
+    g, s, dev, _ = data
+    N, K = 4, 3
+    rng = np.random.default_rng(2)
+    humans = _humans(N, 5, 13)
+    perf = [[bool(b) for b in rng.integers(0, 2, len(h))] for h in humans]
+    perf[2] = [True] * len(humans[2])                       # image 2 has no incorrect answerers: diff group empty
+    predict = {}
+    for name, lo in (("good", 0), ("poor", 2)):
+        predict[name + "_all_actions_prob"] = torch.tensor(g["probs"][lo:lo + N], device=dev, requires_grad=True)
+        predict[name + "_log_normal_mu"] = torch.tensor(g["mu"][lo:lo + N], device=dev, requires_grad=True)
+        predict[name + "_log_normal_sigma2"] = torch.tensor(g["sigma2"][lo:lo + N], device=dev, requires_grad=True)
+    step = AirScstStep(Sampling(convLSTM_length=16, min_length=1, seed=11), dev, rl_sample_number=K)
+    step.set_humans(humans, perf)
+    loss, aux = step(predict)
+    expect = 0.0
+    for name, given in (("good", True), ("poor", False)):
+        a = aux[name]
+        smp = a["samples"]
+        xyd, lens = smp["xyd"].cpu().numpy(), smp["len"].cpu().numpy()
+        table = np.zeros((K, N, 11), dtype=np.float32)
+        for k in range(K):
+            preds = [to_struct(xyd[k * N + i, :lens[k * N + i]]) for i in range(N)]
+            same, diff, flag = O.pairs_eval_scanmatch_performance_related(humans, preds, perf, given)
+            assert flag
+            np.testing.assert_allclose(a["same_table"][k].cpu().numpy(), same, rtol=1e-6, equal_nan=True)
+            np.testing.assert_allclose(a["diff_table"][k].cpu().numpy(), diff, rtol=1e-6, equal_nan=True)
+            table[k, :, 5:7] = np.nan_to_num(same)             # train.py:283: NaN -> 0, then hmean (:300)
+        empty = "diff" if given else "same"                    # image 2: everybody answered correctly
+        assert np.isnan(a[empty + "_table"][:, 2].cpu().numpy()).all() and (a[empty][:, 2] == 0).all()
+        r = OS.scst_loss(predict[name + "_all_actions_prob"].detach().cpu().numpy(),
+                         predict[name + "_log_normal_mu"].detach().cpu().numpy(),
+                         predict[name + "_log_normal_sigma2"].detach().cpu().numpy(),
+                         smp["selected_actions"].cpu().numpy(), smp["durations"].cpu().numpy(),
+                         smp["action_masks"].cpu().numpy(), smp["duration_masks"].cpu().numpy(), table, K)
+        np.testing.assert_allclose(a["same"].cpu().numpy(), OS.hmean_reward(table), rtol=1e-6)
+        expect += float(r["loss"])
+        aux[name]["oracle"] = r
+    assert float(loss) == pytest.approx(expect, rel=RTOL, abs=1e-7)
+    loss.backward()
+    for name in ("good", "poor"):
+        _close(predict[name + "_all_actions_prob"].grad, aux[name]["oracle"]["grad_probs"], name + " grad probs")
+        _close(predict[name + "_log_normal_mu"].grad, aux[name]["oracle"]["grad_mu"], name + " grad mu")
