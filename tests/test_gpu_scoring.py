@@ -125,6 +125,62 @@ def test_human_vs_human_long_paths(S):
     assert np.array_equal(d[:, :, 2], d[:, :, 2].T)
 
 
+@pytest.mark.parametrize("lmax", [24, 64, 100])
+def test_long_scanpaths_on_both_sides(S, lmax):
+    """AiR / COCO human scanpaths are not truncated: both packs with lmax 24 (fast path, 4 columns per lane for
+    the fixation strings), 64 and 100 (warp-per-pair kernel, warps per block reduced to fit the STDE tiles;
+    round 1 failed beyond ~42 with SPB_ERR_UNSUPPORTED)."""
+    from oracle import c_scoring as CO
+    rng = np.random.default_rng(lmax)
+    n = 24
+    H, _ = _random_set(rng, n, lh=(lmax // 2, lmax))
+    H[0] = H[0][:1]; H[1] = H[1][:lmax]
+    cfg = S.ScoreConfig.evaluation(dur_scale=1.0)
+    hp = S.pack_paths(H, cfg, lmax=lmax)
+    gi, pi = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    gi, pi = gi.reshape(-1), pi.reshape(-1)
+    dev = cfg.device
+    out = S.score_pairs(hp, hp, torch.tensor(gi, dtype=torch.int32, device=dev),
+                        torch.tensor(pi, dtype=torch.int32, device=dev), cfg).cpu().numpy()
+    ha, hl = S.pad_paths(H, lmax)
+    ref = CO.score_pairs(ha, hl, ha, hl, gi, pi, threads=os.cpu_count())
+    assert np.array_equal(out[:, :3], ref[:, :3], equal_nan=True)
+    np.testing.assert_allclose(out[:, 3], ref[:, 3], rtol=STDE_RTOL)
+
+
+def test_stale_pair_map_fails_loudly(S):
+    """Pair indices outside their pack (a pair map built for other humans) raise instead of reading out of range."""
+    from scanpaths_b200 import _lib
+    rng = np.random.default_rng(1)
+    H, P = _random_set(rng, 6)
+    cfg = S.ScoreConfig.evaluation(dur_scale=1.0)
+    hp, pp = S.pack_paths(H, cfg), S.pack_paths(P, cfg)
+    dev = cfg.device
+    bad_h = torch.tensor([0, 1, 99], dtype=torch.int32, device=dev)
+    ok_s = torch.tensor([0, 1, 2], dtype=torch.int32, device=dev)
+    with pytest.raises(_lib.SpbError):
+        S.score_pairs(hp, pp, bad_h, ok_s, cfg)
+    out = S.score_pairs(hp, pp, bad_h, ok_s, cfg, check=False).cpu().numpy()
+    assert np.isnan(out[2]).all() and np.isfinite(out[:2, :3]).all()
+
+
+def test_custom_mask_from_array(S):
+    """ScanMatch.maskFromArray (scanmatch.py:199-200): a [Yres, Xres] symbol table replaces the grid."""
+    from oracle.scoring import ScanMatchOracle
+    from scanpaths_b200.utils.evaltools.scanmatch import ScanMatch
+    kw = dict(Xres=320, Yres=240, Xbin=16, Ybin=12, Offset=(0, 0), Threshold=3.5)
+    rng = np.random.default_rng(2)
+    mask = rng.integers(0, 16 * 12, (240, 320)).astype(np.float64)
+    sm, o = ScanMatch(**kw), ScanMatchOracle(**{k: v for k, v in kw.items() if k != "Offset"})
+    sm.maskFromArray(mask)
+    o.mask = mask
+    data = np.stack([rng.uniform(0, 320, 9), rng.uniform(0, 240, 9), rng.uniform(50, 400, 9)], 1)
+    assert np.array_equal(sm.fixationToSequence(data), o.fixationToSequence(data))
+    a = sm.fixationToSequence(data).astype(np.int32)
+    b = sm.fixationToSequence(data[::-1].copy()).astype(np.int32)
+    assert sm.match(a, b)[0] == o.match_score(a, b)
+
+
 def test_gap_value_general_path(S):
     """Non-zero GapValue (never used by the reference's drivers, supported by its class)."""
     from oracle.scoring import ScanMatchOracle
