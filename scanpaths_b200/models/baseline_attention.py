@@ -62,7 +62,12 @@ def _interleave_gates(mats):
 
 
 def prepare_weights(sd, task: str, device):
-    """Reference state_dict (fp32, any device) -> prepared device tensors + the C struct."""
+    """Reference state_dict (fp32, any device) -> prepared device tensors + the C struct.
+    All of the once-per-checkpoint algebra (gate interleaving, Winograd weight transform, the composed head,
+    fp16-pair splits) runs in float64 on the HOST and the results are copied to the device: no library GEMM /
+    convolution kernel (cuBLAS, cuDNN) is ever launched by this package, the only kernels on the device are its own."""
+    target = torch.device(device)
+    device = torch.device("cpu")
     f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
     streams = ["_pos", "_neg"] if task == "AiR" else [""]
     if task == "AiR":
@@ -156,6 +161,7 @@ def prepare_weights(sd, task: str, device):
     t["u_semantic"] = (f("semantic_att.semantic_attention.weight").double().view(1, 512)
                        @ f("semantic_att.semantic_lists.weight").double()).reshape(512).float().contiguous()
     sc = lambda k: float(sd[k].detach().reshape(-1)[0])
+    t = {k: v.contiguous().to(target) for k, v in t.items()}
     w = DecoderWeights()
     for k, v in t.items():
         setattr(w, k, v.data_ptr())
