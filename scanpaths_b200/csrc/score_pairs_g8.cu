@@ -36,6 +36,11 @@ __device__ __forceinline__ double max_f64_bits(double a, double b) {
     const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
     return __longlong_as_double(ia > ib ? ia : ib);
 }
+// min of two non-negative doubles (or +inf), same argument as above
+__device__ __forceinline__ double min_f64_bits(double a, double b) {
+    const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    return __longlong_as_double(ia < ib ? ia : ib);
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -268,7 +273,7 @@ __device__ __forceinline__ double stde_g8(const double *ax, const double *ay, in
                 if (on && j < nh) {
                     const double w = wp[j] + dp[j];
                     wp[j] = w;
-                    best = fmin(best, w);
+                    best = min_f64_bits(best, w);       // distances are >= 0
                 }
             }
             if (on) acc += best / (double)k;

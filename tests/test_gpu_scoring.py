@@ -332,3 +332,57 @@ def test_mirror_air_performance_related_drivers(S, golden_dir):
     np.testing.assert_allclose(flat(m), g["epr_mean"], rtol=2e-6)
     np.testing.assert_allclose(flat(s), g["epr_std"], rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(np.array(per)[:, 5:], g["epr_per_image"], rtol=1e-12)
+
+
+def test_reduce_pairs_counts_length_rule_accumulators(S):
+    """spb_reduce_pairs in one pass: padded subjects skipped (divisor = real subject count), the < 3 fixations rule
+    from the path lengths, mean over the surviving rows (AiR variant), per-group validity, and the `evaluation`
+    accumulators -- against numpy, and bit-reproducible from call to call (no floating-point atomics)."""
+    rng = np.random.default_rng(5)
+    K, N, Sn = 7, 9, 6
+    G = K * N
+    sc = rng.uniform(0.05, 1, (G * Sn, 4)); sc[:, 2] = rng.integers(0, 17, G * Sn)
+    counts = rng.integers(0, Sn + 1, N).astype(np.int32); counts[0] = Sn; counts[1] = 0
+    len_h = rng.integers(1, 8, N * Sn).astype(np.int32)
+    len_s = rng.integers(1, 8, G).astype(np.int32)
+    pair_h = np.tile((np.arange(N)[:, None] * Sn + np.arange(Sn)[None, :]).reshape(-1), K).astype(np.int32)
+    pair_s = np.repeat(np.arange(G), Sn).astype(np.int32)
+    dev = torch.device("cuda")
+    t = lambda a: torch.tensor(a, device=dev)
+    acc = S.new_accumulator(dev)
+    args = dict(n_images=N, group_count=t(counts), pair_h=t(pair_h), pair_s=t(pair_s), len_h=t(len_h), len_s=t(len_s),
+                min_len_valid=3)
+    tab, rew, gv = S.reduce_pairs(t(sc), Sn, acc=acc, **args)
+    first = acc[:16].clone()
+    acc2 = S.new_accumulator(dev)
+    tab2, rew2, gv2 = S.reduce_pairs(t(sc), Sn, acc=acc2, **args)
+    assert torch.equal(first, acc2[:16]) and torch.equal(torch.nan_to_num(tab), torch.nan_to_num(tab2))   # reproducible
+    S.reduce_pairs(t(sc), Sn, acc=acc, **args)                       # accumulates over calls
+    np.testing.assert_allclose(acc[:16].cpu().numpy(), 2 * first.cpu().numpy(), rtol=1e-14)
+    tab, rew, gv, a = tab.cpu().numpy(), rew.cpu().numpy(), gv.cpu().numpy(), first.cpu().numpy()
+    tabk, _, _ = S.reduce_pairs(t(sc), Sn, mean_over_kept=True, **args)
+    tabk = tabk.cpu().numpy()
+    rows_all, best = [], []
+    for g in range(G):
+        img = g % N
+        c = int(counts[img])
+        rows = sc[g * Sn:g * Sn + c]
+        ok = (len_h[pair_h[g * Sn:g * Sn + c]] >= 3) & (len_s[g] >= 3)
+        if c:
+            rows_all.append(rows); best.append([rows[:, 2].min(), rows[:, 3].max()])
+        if not ok.any():
+            assert np.isnan(tab[g]).all() and np.isnan(rew[g]) and gv[g] == 0
+            continue
+        r = rows[ok]
+        exp = np.array([r[:, 1].sum() / c, r[:, 0].sum() / c, r[:, 2].sum() / c, r[:, 3].sum() / c, r[:, 2].min(),
+                        r[:, 3].max()], dtype=np.float32)
+        np.testing.assert_array_equal(tab[g, 5:], exp)
+        np.testing.assert_allclose(tabk[g, 5:9], exp[:4] * c / ok.sum(), rtol=1e-6)
+        assert gv[g] == 1 and (tab[g, :5] == 0).all()
+        assert rew[g] == pytest.approx(2 / (1 / float(exp[0]) + 1 / float(exp[1])), rel=1e-12)
+    rows_all, best = np.concatenate(rows_all, 0), np.array(best)
+    np.testing.assert_allclose(a[0:4], rows_all.sum(0), rtol=1e-12)
+    np.testing.assert_allclose(a[4:8], (rows_all ** 2).sum(0), rtol=1e-12)
+    np.testing.assert_allclose(a[8:10], best.sum(0), rtol=1e-12)
+    np.testing.assert_allclose(a[10:12], (best ** 2).sum(0), rtol=1e-12)
+    assert a[12] == len(rows_all) and a[13] == len(best) and a[14] == gv.sum()
