@@ -358,6 +358,15 @@ typedef struct spb_decoder_io {
 int64_t spb_decoder_workspace_bytes(int32_t n_images, int32_t n_streams, int32_t n_heads, int32_t steps);
 int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream);
 
+/* f3, last layer of the once-per-image encoder: d_vf = relu(sal_conv(d_x)) -- Conv2d(2048, 512, 3, padding 1) on
+ * the dilated ResNet-50's [N, 2048, 30, 40] map (OSIE/models/baseline_attention.py:194, :328), as a tcgen05
+ * implicit GEMM with fp32-equivalent fp16 operand pairs (w: [512, 9*2048], K index (ky*3+kx)*2048 + ci, prepared
+ * like the decoder's conv weights).  d_x, d_vf are channel-major (NCHW) like the reference's tensors; the
+ * workspace (spb_sal_conv_workspace_bytes) holds the NHWC operand pairs of d_x. */
+int64_t spb_sal_conv_workspace_bytes(int32_t n_images);
+int spb_sal_conv(const float *d_x, const void *d_w_hi, const void *d_w_lo, const float *d_bias, float inv_scale,
+                 int32_t n_images, void *d_workspace, int64_t workspace_bytes, float *d_vf, spb_stream stream);
+
 /* One implicit-GEMM convolution on its own (unit tests / profiling of the kernel):
  * d_out[(n*1200+p)*ldo + col] = inv_scale * conv_ks(a, w)[p, col] + bias[col]  (ks = 1, 3, 5; operand pairs
  * x = hi + lo/2^11, a NHWC [N,30,40,512], w [rows, ks*ks*512]). */

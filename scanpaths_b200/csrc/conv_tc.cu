@@ -57,7 +57,8 @@ constexpr int kOutBytes = kOutRows * kTileCh * 4;         // 15 KB staging per p
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kOutBytes;
 constexpr int kTmemCols = 512, kCorrCol = 256;
 constexpr int kThreads = 320;
-constexpr int kChunkKB = kE / kBlockK;                    // k-blocks per drained chunk: one filter tap
+constexpr int kChunkKB = 512 / kBlockK;                   // k-blocks per drained chunk: 512 input channels of one filter tap
+                                                          // (32 accumulation steps: what the truncation compensation is measured for)
 constexpr int kHalfPix = kTilePix / 2;                    // 120 pixels of totals per drain thread
 static_assert(kHalfPix % kOutRows == 0, "store boxes must tile the pixel half");
 
@@ -140,7 +141,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int KS>
+template <int KS, int CIN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -158,7 +159,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t out_smem = bar0 + 256;                         // 2 x 15 KB TMA-store staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kNumKB = KS * KS * (kE / kBlockK);
+    constexpr int kKBperTap = CIN / kBlockK;              // CIN = 512 (decoder) or 2048 (the encoder's sal_conv)
+    constexpr int kNumKB = KS * KS * kKBperTap;
     constexpr int kNumChunks = kNumKB / kChunkKB;
     constexpr int kPad = KS / 2;
 
@@ -197,7 +199,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 for (int kb = 0; kb < kNumKB; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-                    const int tap = kb / (kE / kBlockK), cb = kb % (kE / kBlockK);
+                    const int tap = kb / kKBperTap, cb = kb % kKBperTap;
                     const int ky = tap / KS, kx = tap % KS;
                     const uint32_t sa = base + s * kStageBytes;
                     mbar_expect_tx(full_bar(s), kStageBytes);
@@ -369,13 +371,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const float bias = a.bias ? a.bias[row_base + r] : 0.0f;
             const uint32_t stage_out = out_smem + half * kOutBytes;
             const int64_t row0 = (int64_t)img * rows_per_img + p_tile * kTilePix + half * kHalfPix;
+            if (a.nchw) {
+                // channel-major output [img][col][pixel] (what the decoder takes as visual_feature): this thread's
+                // 120 pixels of its channel are contiguous
+                float *dst = a.out + ((int64_t)img * a.cols + c_tile * kTileCh + r) * rows_per_img + p_tile * kTilePix + half * kHalfPix;
+#pragma unroll
+                for (int j = 0; j < kHalfPix; j += 4) {
+                    float4 v;
+                    v.x = tot[j] * a.inv_scale + bias; v.y = tot[j + 1] * a.inv_scale + bias;
+                    v.z = tot[j + 2] * a.inv_scale + bias; v.w = tot[j + 3] * a.inv_scale + bias;
+                    if (a.relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+                    *reinterpret_cast<float4 *>(dst + j) = v;
+                }
+                continue;
+            }
 #pragma unroll
             for (int rr = 0; rr < kHalfPix / kOutRows; ++rr) {
                 if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
                 named_bar_sync(1 + half, 128);
 #pragma unroll
                 for (int j = 0; j < kOutRows; ++j) {
-                    const float v = tot[rr * kOutRows + j] * a.inv_scale + bias;
+                    float v = tot[rr * kOutRows + j] * a.inv_scale + bias;
+                    if (a.relu) v = fmaxf(v, 0.0f);
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage_out + (uint32_t)(j * kTileCh + r) * 4), "f"(v) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -617,9 +634,9 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images, int rows_per_img) {
-    const cuuint64_t dims[4] = {(cuuint64_t)kE, (cuuint64_t)kW, (cuuint64_t)(rows_per_img / kW), (cuuint64_t)n_images};
-    const cuuint64_t strides[3] = {(cuuint64_t)kE * 2, (cuuint64_t)kW * kE * 2, (cuuint64_t)rows_per_img * kE * 2};
+static int make_map_a(CUtensorMap *m, const __half *ptr, int n_images, int rows_per_img, int cin) {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)kW, (cuuint64_t)(rows_per_img / kW), (cuuint64_t)n_images};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)kW * cin * 2, (cuuint64_t)rows_per_img * cin * 2};
     const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kW, (cuuint32_t)(kTilePix / kW), 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
@@ -660,7 +677,8 @@ int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
     // be any multiple of 240 rows (plain batched GEMM: out[b][row][col] = sum_k a[b][row][k] w[base_b + col][k])
     const int rows = a.rows_per_img;
     if (a.cols % kTileCh != 0 || (a.ks != 1 && a.ks != 3 && a.ks != 5) || a.ldo % 4 != 0 || ((uintptr_t)a.out & 15) != 0 ||
-        a.w_row_div < 1 || rows <= 0 || rows % kTilePix != 0 || (a.ks != 1 && rows != kHW)) {
+        a.w_row_div < 1 || rows <= 0 || rows % kTilePix != 0 || (a.ks != 1 && rows != kHW) ||
+        (a.cin != kE && !(a.cin == 2048 && a.ks == 3)) || (a.nchw && a.w_row_base != nullptr)) {
         set_error("conv_gemm_tc: cols must be a multiple of %d, rows per image of %d, ks 1, 3 or 5, out 16-byte aligned",
                   kTileCh, kTilePix);
         return SPB_ERR_ARG;
@@ -669,10 +687,10 @@ int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
         set_error("conv_gemm_tc: cuTensorMapEncodeTiled not available from the driver");
         return SPB_ERR_CUDA;
     }
-    const int64_t K = (int64_t)a.ks * a.ks * kE;
+    const int64_t K = (int64_t)a.ks * a.ks * a.cin;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo;
-    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows);
-    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows);
+    int rc = make_map_a(&ma_hi, a.a_hi, a.n_images, rows, a.cin);
+    if (!rc) rc = make_map_a(&ma_lo, a.a_lo, a.n_images, rows, a.cin);
     if (!rc) rc = make_map_b(&mw_hi, a.w_hi, a.w_rows, K);
     if (!rc) rc = make_map_b(&mw_lo, a.w_lo, a.w_rows, K);
     if (!rc) rc = make_map_out(&mo, a.out, a.ldo, (int64_t)a.n_images * rows, kTileCh);
@@ -688,12 +706,13 @@ int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
     }
     const int num_tiles = (int)tiles64;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();       // persistent: one CTA per SM
-#define SPB_LAUNCH_TC(KS_)                                                                                          \
-    SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-    conv_gemm_tc_kernel<KS_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
-    if (a.ks == 1) { SPB_LAUNCH_TC(1); }
-    else if (a.ks == 3) { SPB_LAUNCH_TC(3); }
-    else { SPB_LAUNCH_TC(5); }
+#define SPB_LAUNCH_TC(KS_, CIN_)                                                                                          \
+    SPB_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<KS_, CIN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+    conv_gemm_tc_kernel<KS_, CIN_><<<grid, kThreads, kSmemBytes, s>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo, a, num_tiles, nct, pt, rows)
+    if (a.cin == 2048) { SPB_LAUNCH_TC(3, 2048); }
+    else if (a.ks == 1) { SPB_LAUNCH_TC(1, 512); }
+    else if (a.ks == 3) { SPB_LAUNCH_TC(3, 512); }
+    else { SPB_LAUNCH_TC(5, 512); }
 #undef SPB_LAUNCH_TC
     SPB_LAUNCH_CHECK();
     return SPB_OK;

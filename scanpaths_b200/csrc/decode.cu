@@ -1087,6 +1087,40 @@ extern "C" int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void 
     return conv_gemm(a, use_tensor_cores != 0, (cudaStream_t)stream);
 }
 
+#define SPB_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != SPB_OK) return rc__; \
+    } while (0)
+
+// f3 (the last layer of the once-per-image encoder): visual_feature = relu(sal_conv(x))
+// (OSIE/models/baseline_attention.py:194, :328): Conv2d(2048, 512, 3, padding = 1) on the 30 x 40 ResNet map as
+// the same direct implicit GEMM as the x-gates (K = 9 * 2048, accumulators drained every 512 channels),
+// fp32-equivalent fp16 operand pairs, bias + ReLU in the epilogue, output channel-major like the reference's.
+extern "C" int64_t spb_sal_conv_workspace_bytes(int32_t n_images) {
+    return n_images > 0 ? (int64_t)n_images * kHW * 2048 * 2 * 2 : 0;
+}
+
+extern "C" int spb_sal_conv(const float *d_x, const void *d_w_hi, const void *d_w_lo, const float *d_bias,
+                            float inv_scale, int32_t n_images, void *d_workspace, int64_t workspace_bytes,
+                            float *d_vf, spb_stream stream) {
+    SPB_CHECK_ARG(d_x && d_w_hi && d_w_lo && d_vf && d_workspace, "null device pointer");
+    SPB_CHECK_ARG(n_images > 0, "bad sizes");
+    SPB_CHECK_ARG(((uintptr_t)d_workspace & 1023) == 0 && ((uintptr_t)d_vf & 15) == 0, "workspace must be 1024-byte, output 16-byte aligned");
+    if (workspace_bytes < spb_sal_conv_workspace_bytes(n_images)) {
+        set_error("spb_sal_conv: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+                  (long long)spb_sal_conv_workspace_bytes(n_images));
+        return SPB_ERR_WORKSPACE;
+    }
+    constexpr int kCin = 2048;
+    __half *x_hi = (__half *)d_workspace, *x_lo = x_hi + (int64_t)n_images * kHW * kCin;
+    SPB_TRY(spb_split_fp16(d_x, x_hi, x_lo, n_images, kCin, kHW, 1, 1.0f, stream));
+    ConvGemmArgs a{x_hi, x_lo, (const __half *)d_w_hi, (const __half *)d_w_lo, nullptr, kE, d_bias, d_vf, kE, n_images, kE, 3,
+                   inv_scale};
+    a.cin = kCin; a.relu = 1; a.nchw = 1;
+    return conv_gemm_tc(a, (cudaStream_t)stream);
+}
+
 extern "C" int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
                              int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream) {
     SPB_CHECK_ARG(d_u_hi && d_u_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
@@ -1094,11 +1128,6 @@ extern "C" int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void 
                         d_out, rows_pad, cols, inv_scale, (cudaStream_t)stream);
 }
 
-#define SPB_TRY(expr)                 \
-    do {                              \
-        int rc__ = (expr);            \
-        if (rc__ != SPB_OK) return rc__; \
-    } while (0)
 
 extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io, spb_stream stream) {
     SPB_CHECK_ARG(w && io, "null struct pointer");

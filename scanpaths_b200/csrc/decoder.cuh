@@ -39,6 +39,9 @@ struct ConvGemmArgs {
     int w_row_div = 1;            // w_row_base is given in units of w_row_div rows
     int rows_per_img = kHW;       // ks = 1 only: any multiple of 240 (the kernel as a plain batched GEMM)
     float trunc_fix = 0.0f;       // set by conv_gemm_tc from acc_trunc_fix()
+    int cin = kE;                 // input channels: 512, or 2048 for the encoder's sal_conv (ks = 3, tensor-core route)
+    int relu = 0;                 // epilogue: max(., 0)
+    int nchw = 0;                 // epilogue: channel-major output out[(n*cols + col)*rows_per_img + p] (ldo unused)
 };
 
 // Column order of the 2048 gate columns: [64-channel block cb][32-channel half][gate i,f,o,g][32].

@@ -455,10 +455,44 @@ class baseline(nn.Module):
         return self
 
     def encode(self, images):
-        return F.relu(self.sal_conv(self.resnet(images)))
+        """The once-per-image encoder (baseline_attention.py:327-328): the dilated ResNet-50 stays in PyTorch;
+        its last layer, relu(sal_conv(.)) -- 22.65 GFLOP per image, as much as the whole x-gate convolution --
+        runs on the tensor cores through spb_sal_conv when the model lives on a CUDA device."""
+        x = self.resnet(images)
+        if not x.is_cuda:
+            return F.relu(self.sal_conv(x))                # CPU tensors: plain PyTorch (tests/test_encoder_reference.py)
+        return self.sal_conv_cuda(x)
+
+    def sal_conv_cuda(self, x):
+        """relu(sal_conv(x)) for x [N,2048,30,40] f32 on the device -> [N,512,30,40] f32 (csrc/conv_tc.cu)."""
+        lib = _lib.load()
+        x = x.detach().to(torch.float32).contiguous()
+        N = x.shape[0]
+        assert x.shape[1:] == (2048, 30, 40), "sal_conv input must be [N,2048,30,40]"
+        dev = x.device
+        if getattr(self, "_sal_prepared", None) is None or self._sal_prepared[0] != dev:
+            if self.use_tensor_cores:
+                calibrate_acc_trunc_fix(dev)
+            w = self.sal_conv.weight.detach().to("cpu", torch.float32)
+            hi, lo, inv = split_pair(_conv_to_gemm(w))     # [512, 9*2048], K index (ky*3+kx)*2048 + ci
+            self._sal_prepared = (dev, hi.to(dev), lo.to(dev), self.sal_conv.bias.detach().to(dev, torch.float32).contiguous(), inv)
+        _, w_hi, w_lo, bias, inv = self._sal_prepared
+        out = torch.empty((N, E, 30, 40), dtype=torch.float32, device=dev)
+        for n0 in range(0, N, self.wave):                  # waves bound the operand workspace (9.8 MB per image)
+            n = min(N, n0 + self.wave) - n0
+            nbytes = lib.spb_sal_conv_workspace_bytes(n)
+            if getattr(self, "_sal_ws", None) is None or self._sal_ws.numel() < nbytes + 1024 or self._sal_ws.device != dev:
+                self._sal_ws = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=dev)
+            off = (-self._sal_ws.data_ptr()) % 1024
+            with torch.cuda.device(dev):
+                _lib.check(lib.spb_sal_conv(x[n0:n0 + n].data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), bias.data_ptr(), inv, n,
+                                            self._sal_ws.data_ptr() + off, self._sal_ws.numel() - off,
+                                            out[n0:n0 + n].data_ptr(), _lib.current_stream()), "spb_sal_conv")
+        return out
 
     def load_state_dict(self, state_dict, strict=False, **kw):
         self._decoder = None
+        self._sal_prepared = None
         own = {k: v for k, v in state_dict.items() if not k.startswith(("resnet.", "sal_conv."))} \
             if self.resnet is None else state_dict
         return super().load_state_dict(own, strict=strict, **kw)

@@ -305,3 +305,25 @@ def test_decode_graph_replay_equals_eager(lib):
         for a, b in zip(eager, graphed):
             assert torch.equal(a, b)
     assert len(dec._graphs) == 1
+
+
+def test_sal_conv_tensor_core_vs_torch_fp64(lib):
+    """f3, the encoder's last layer: relu(sal_conv(x)) -- Conv2d(2048, 512, 3, padding 1) (baseline_attention.py:194,
+    :328) -- through spb_sal_conv (tcgen05, K = 9 * 2048) against torch's float64 convolution; channel-major in,
+    channel-major out, waves smaller than the batch included."""
+    from scanpaths_b200.models.baseline_attention import baseline
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    m = baseline(task="OSIE", wave=2)
+    m.sal_conv = torch.nn.Conv2d(2048, 512, kernel_size=3, padding=1, stride=1, bias=True)
+    torch.nn.init.xavier_normal_(m.sal_conv.weight)
+    torch.nn.init.normal_(m.sal_conv.bias, std=0.1)
+    m = m.cuda()
+    x = torch.randn((3, 2048, 30, 40), generator=g, device=dev).clamp_min_(0)      # a post-ReLU ResNet map
+    got = m.sal_conv_cuda(x)
+    ref = F.relu(F.conv2d(x.double(), m.sal_conv.weight.double(), m.sal_conv.bias.double(), padding=1))
+    err = (got.double() - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    print("sal_conv tcgen05: max abs err %.3e (max |out| %.2f), zeros %.2f" % (err, mag, float((got == 0).float().mean())))
+    assert got.shape == (3, 512, 30, 40) and err < 1e-5 * mag, (err, mag)
+    assert torch.equal(got == 0, ref == 0) or float(((got == 0) != (ref == 0)).float().mean()) < 1e-4
