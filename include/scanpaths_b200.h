@@ -379,9 +379,10 @@ int spb_conv_gemm(const void *d_a_hi, const void *d_a_lo, const void *d_w_hi, co
  * p = 4j + i with i = 0..3 the row position (F(2,3)) and j = 0..5 the column position (F(4,3)):
  *   m[i][j] = u[p] . w[p]^T  (K = 512),  out[2j] = m[0][j]+m[1][j]+m[2][j],  out[2j+1] = m[1][j]-m[2][j]-m[3][j]
  * d_u  [24][rows_pad][512], d_w [24*cols][512]: fp16 pairs x = hi + lo/2^11; rows_pad, cols % 128 == 0;
- * d_out[((k*cols/128 + col/128)*rows_pad + row)*128 + col%128], k = 0..11, scaled by inv_scale. */
+ * d_out[((k*cols/128 + col/128)*rows_pad + row)*128 + col%128], k = 0..11, scaled by inv_scale.
+ * fine_drain != 0: accumulators are drained every 8 k-steps instead of 32 (less truncation noise, 4x the TMEM reads). */
 int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
-                  int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream);
+                  int64_t rows_pad, int32_t cols, float inv_scale, int32_t fine_drain, spb_stream stream);
 
 /* Compensation of the tensor core's truncating fp32 accumulation (csrc/decoder.cuh): every drained "main"
  * accumulator x becomes x + x * fix.  Default 5.5e-7 (measured on B200, 32 accumulation steps, mixed-sign
@@ -389,6 +390,8 @@ int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, co
  * an exact float64 product and installs the result here.  Process-wide. */
 float spb_get_acc_trunc_fix(void);
 int spb_set_acc_trunc_fix(float fix);
+float spb_get_acc_trunc_fix_fine(void);          /* the same for the 8-k-step accumulators (spb_wino_gemm fine_drain) */
+int spb_set_acc_trunc_fix_fine(float fix);
 
 /* fp32 -> (hi, lo) fp16 pair: x*scale = hi + lo / 2^11.  NCHW [N,C,HW] -> NHWC when `transpose`. */
 int spb_split_fp16(const float *d_x, void *d_hi, void *d_lo, int64_t n_outer, int32_t C, int32_t HW,

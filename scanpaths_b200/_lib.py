@@ -93,11 +93,13 @@ SYMBOLS.update({
     "spb_decode": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderIO), C.c_void_p]),
     "spb_conv_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                                    C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
-    "spb_wino_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "spb_wino_gemm": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "spb_sal_conv_workspace_bytes": (C.c_int64, [C.c_int32]),
     "spb_sal_conv": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "spb_get_acc_trunc_fix": (C.c_float, []),
     "spb_set_acc_trunc_fix": (C.c_int, [C.c_float]),
+    "spb_get_acc_trunc_fix_fine": (C.c_float, []),
+    "spb_set_acc_trunc_fix_fine": (C.c_int, [C.c_float]),
     "spb_split_fp16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_float, C.c_void_p]),
 })

@@ -469,6 +469,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// CHUNKS: accumulator chunks per position.  1 = the whole K = 512 of a position in one [main | corr] buffer (32
+// accumulation steps; the h-gates).  4 = a fresh buffer every 2 k-blocks (8 accumulation steps), folded into the
+// running sums by the drain warps with round-to-nearest adds: less truncation noise for the output transform to
+// amplify -- for the loop-invariant x-gates, whose error is coherent over the 16 steps (decode.cu).
+template <int CHUNKS>
 __global__ void __launch_bounds__(kThreads, 1)
 wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_constant__ CUtensorMap tmU_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -532,12 +537,12 @@ wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_con
         if (lane == 0) {
             uint32_t it = 0, pc = 0;                       // pc: positions issued so far (buffer ring index)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int i = 0; i < wg::kPosI; ++i, ++pc) {
+                for (int ic = 0; ic < wg::kPosI * CHUNKS; ++ic, ++pc) {       // (position i, chunk) pairs
                     const int buf = pc & (wg::kNumBuf - 1);
                     const uint32_t d_main = tmem_base + buf * 2 * wg::kAccCols, d_corr = d_main + wg::kAccCols;
                     mbar_wait(acc_empty_bar(buf), ((pc / wg::kNumBuf) & 1) ^ 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+                    for (int kb = 0; kb < kNumKB / CHUNKS; ++kb, ++it) {
                         const int s = it % wg::kStages;
                         mbar_wait(full_bar(s), (it / wg::kStages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -568,7 +573,9 @@ wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_con
             const int c_tile = tile % nct, tb = (tile / nct) % ntb, j = tile / (nct * ntb);
             float sa[kMine], sb[kMine];
 #pragma unroll
-            for (int i = 0; i < wg::kPosI; ++i, ++pc) {
+            for (int ic = 0; ic < wg::kPosI * CHUNKS; ++ic, ++pc) {
+                const int i = ic / CHUNKS;
+                const bool first = (ic % CHUNKS) == 0;        // first chunk of its position
                 const int buf = pc & (wg::kNumBuf - 1);
                 const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * wg::kAccCols + half * kMine;
                 mbar_wait(acc_full_bar(buf), (pc / wg::kNumBuf) & 1);
@@ -586,8 +593,8 @@ wino_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_con
                     for (int e = 0; e < 16; ++e) {
                         const float mm = __uint_as_float(vm[e >> 3][e & 7]);
                         const float m = fmaf(__uint_as_float(vc[e >> 3][e & 7]), 1.0f / kLoScale, fmaf(mm, trunc_fix, mm));
-                        if (i == 0) sa[c + e] = m;
-                        else if (i == 1) { sa[c + e] += m; sb[c + e] = m; }
+                        if (i == 0) sa[c + e] = first ? m : sa[c + e] + m;
+                        else if (i == 1) { sa[c + e] += m; sb[c + e] = first ? m : sb[c + e] + m; }
                         else if (i == 2) { sa[c + e] += m; sb[c + e] -= m; }
                         else sb[c + e] -= m;
                     }
@@ -722,7 +729,7 @@ int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
 //   u  [24][rows_pad][512] fp16 pairs (hi + lo/2^11), position p = 4j + i;  w [24 * cols][512] fp16 pairs;
 //   out [12][cols/128][rows_pad][128] fp32.  rows_pad % 128 == 0, cols % 128 == 0.
 int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
-                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s) {
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain) {
     using namespace tc;
     constexpr int kPos = wg::kPosI * wg::kPosJ;
     if (rows_pad <= 0 || rows_pad % wg::kTileRows != 0 || cols <= 0 || cols % kTileCh != 0 || ((uintptr_t)out & 15) != 0) {
@@ -760,9 +767,15 @@ int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, con
     }
     const int num_tiles = (int)(wg::kPosJ * nct * ntb);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
-    wino_gemm_tc_kernel<<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb, cols,
-                                                              rows_pad, inv_scale, acc_trunc_fix());
+    if (fine_drain) {
+        SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
+        wino_gemm_tc_kernel<4><<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb,
+                                                                     cols, rows_pad, inv_scale, acc_trunc_fix_fine());
+    } else {
+        SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
+        wino_gemm_tc_kernel<1><<<grid, kThreads, wg::kSmemBytes, s>>>(mu_hi, mu_lo, mw_hi, mw_lo, out, num_tiles, nct, (int)ntb,
+                                                                     cols, rows_pad, inv_scale, acc_trunc_fix());
+    }
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }

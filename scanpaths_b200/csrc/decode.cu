@@ -1041,8 +1041,18 @@ using namespace spb;
 
 namespace spb {
 static float g_acc_trunc_fix = kAccTruncFixDefault;
+static float g_acc_trunc_fix_fine = 0.25f * kAccTruncFixDefault;     // 8 accumulation steps instead of 32
 float acc_trunc_fix() { return g_acc_trunc_fix; }
+float acc_trunc_fix_fine() { return g_acc_trunc_fix_fine; }
 }  // namespace spb
+
+extern "C" float spb_get_acc_trunc_fix_fine(void) { return g_acc_trunc_fix_fine; }
+
+extern "C" int spb_set_acc_trunc_fix_fine(float fix) {
+    SPB_CHECK_ARG(fix >= 0.0f && fix < 1e-4f, "the accumulator truncation compensation must lie in [0, 1e-4)");
+    g_acc_trunc_fix_fine = fix;
+    return SPB_OK;
+}
 
 extern "C" float spb_get_acc_trunc_fix(void) { return g_acc_trunc_fix; }
 
@@ -1122,10 +1132,10 @@ extern "C" int spb_sal_conv(const float *d_x, const void *d_w_hi, const void *d_
 }
 
 extern "C" int spb_wino_gemm(const void *d_u_hi, const void *d_u_lo, const void *d_w_hi, const void *d_w_lo, float *d_out,
-                             int64_t rows_pad, int32_t cols, float inv_scale, spb_stream stream) {
+                             int64_t rows_pad, int32_t cols, float inv_scale, int32_t fine_drain, spb_stream stream) {
     SPB_CHECK_ARG(d_u_hi && d_u_lo && d_w_hi && d_w_lo && d_out, "null device pointer");
     return wino_gemm_tc((const __half *)d_u_hi, (const __half *)d_u_lo, (const __half *)d_w_hi, (const __half *)d_w_lo,
-                        d_out, rows_pad, cols, inv_scale, (cudaStream_t)stream);
+                        d_out, rows_pad, cols, inv_scale, (cudaStream_t)stream, fine_drain != 0);
 }
 
 
@@ -1150,8 +1160,10 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     //    over the recurrence, and the Winograd form's is 2x larger (fp32 accumulation noise amplified by the
     //    output transform): measured end to end, Winograd x-gates double the error of the probabilities;
     // 2: direct implicit GEMM for both;  3: Winograd for both (the round-1 product path, kept for comparison)
-    const bool wino = io->use_tensor_cores == 1 || io->use_tensor_cores == 3;
-    const bool wino_x = io->use_tensor_cores == 3;
+    // 4: Winograd for both, the x-gate GEMM with 8-k-step accumulators (wino_gemm_tc_kernel<4>)
+    const bool wino = io->use_tensor_cores == 1 || io->use_tensor_cores == 3 || io->use_tensor_cores == 4;
+    const bool wino_x = io->use_tensor_cores == 3 || io->use_tensor_cores == 4;
+    const bool wino_x_fine = io->use_tensor_cores == 4;
     const int64_t NP = N * kHW;
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
@@ -1166,7 +1178,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         wino_input_kernel<<<(unsigned)(N * kTilesY), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
         SPB_LAUNCH_CHECK();
         SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->wwx_hi, (const __half *)w->wwx_lo, ws.wm, ws.rows_pad,
-                             kGateCols, w->inv_scale_wx, s));
+                             kGateCols, w->inv_scale_wx, s, wino_x_fine));
         wino_output_kernel<<<dim3(kTilesY, (unsigned)N, kGateCols / 128), 128, 0, s>>>(ws.wm, ws.rows_pad, w->bias_gate, ws.xg);
         SPB_LAUNCH_CHECK();
     } else {

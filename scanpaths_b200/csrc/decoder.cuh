@@ -20,7 +20,8 @@ constexpr float kLoScale = 2048.0f; // lo half is stored as (x - hi) * 2^11
 // the device at decoder construction by a probe GEMM (models/baseline_attention.py::calibrate_acc_trunc_fix)
 // so that another SKU / driver with a different accumulation cannot silently shift parity.
 constexpr float kAccTruncFixDefault = 5.5e-7f;
-float acc_trunc_fix();                 // current value (spb_set_acc_trunc_fix)
+float acc_trunc_fix();                 // current value (spb_set_acc_trunc_fix), accumulators of 32 k-steps
+float acc_trunc_fix_fine();            // the same for the 8-k-step accumulators of wino_gemm_tc_kernel<4>
 
 // One implicit-GEMM convolution:  out[(n*1200+p)*ldo + col] = inv_scale * conv(a, w)[p, col] (+ bias[col])
 //   a  = a_hi + a_lo / 2^11   fp16 NHWC [N,30,40,512]
@@ -55,6 +56,6 @@ int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s);     // tcgen05 / TMEM /
 // the 24 Winograd F(2x4,3x3) per-position GEMMs + the row half of the output transform (conv_tc.cu):
 // u [24][rows_pad][512], w [24*cols][512] fp16 pairs (position 4j+i) -> out [12][cols/128][rows_pad][128] fp32
 int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
-                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s);
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain = false);
 
 }  // namespace spb

@@ -179,7 +179,7 @@ def prepare_weights(sd, task: str, device):
 _ACC_FIX_DONE = {}
 
 
-def measure_acc_trunc_bias(device, one_signed=False, seed=12345):
+def measure_acc_trunc_bias(device, one_signed=False, seed=12345, fine=False):
     """Relative shrink of the tensor-core accumulation, measured with a probe through spb_wino_gemm (fix = 0):
     24 GEMMs [128 x 512] x [512 x 128] on seeded operands, compared with the exact float64 value of what the
     kernel sums (hi*hi + (hi*lo + lo*hi) / 2^11 of the same fp16 pairs; numpy on the host: no GPU library call).
@@ -212,15 +212,17 @@ def measure_acc_trunc_bias(device, one_signed=False, seed=12345):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d = [t(x) for x in (u_hi, u_lo, w_hi, w_lo)]
     out = torch.empty((12, cols // 128, rows, 128), dtype=torch.float32, device=dev)
-    old = lib.spb_get_acc_trunc_fix()
-    _lib.check(lib.spb_set_acc_trunc_fix(0.0), "spb_set_acc_trunc_fix")
+    getter, setter = (lib.spb_get_acc_trunc_fix_fine, lib.spb_set_acc_trunc_fix_fine) if fine else \
+        (lib.spb_get_acc_trunc_fix, lib.spb_set_acc_trunc_fix)
+    old = getter()
+    _lib.check(setter(0.0), "spb_set_acc_trunc_fix")
     try:
         with torch.cuda.device(dev):
             _lib.check(lib.spb_wino_gemm(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), _lib.ptr(out),
-                                         rows, cols, 1.0 / scale, _lib.current_stream()), "spb_wino_gemm")
+                                         rows, cols, 1.0 / scale, 1 if fine else 0, _lib.current_stream()), "spb_wino_gemm")
         got = out.permute(0, 2, 1, 3).reshape(12, rows, cols).double().cpu().numpy()
     finally:
-        lib.spb_set_acc_trunc_fix(old)
+        setter(old)
     return 1.0 - float((got * ref).sum() / (ref * ref).sum())
 
 
@@ -247,6 +249,10 @@ def calibrate_acc_trunc_fix(device):
         else:
             fix = b
     _lib.check(lib.spb_set_acc_trunc_fix(fix), "spb_set_acc_trunc_fix")
+    if not env:                                              # the 8-k-step accumulators of the fine-drain GEMM
+        bf = measure_acc_trunc_bias(device, fine=True)
+        if 0.0 <= bf < 5e-6:
+            _lib.check(lib.spb_set_acc_trunc_fix_fine(bf), "spb_set_acc_trunc_fix_fine")
     _ACC_FIX_DONE[key] = fix
     return fix
 

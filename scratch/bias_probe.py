@@ -9,7 +9,7 @@ dev = torch.device('cuda')
 
 def split_dev(x):
     hi = torch.empty_like(x, dtype=torch.float16); lo = torch.empty_like(hi)
-    _lib.check(lib.spb_split_fp16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), 1, 1, 0, 1.0, _lib.current_stream()))
+    _lib.check(lib.spb_split_fp16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), 1, 1, 0, 1.0, 0, _lib.current_stream()))
     return hi, lo
 
 def fit(got, ref):
@@ -26,7 +26,7 @@ def wino_case(name, u, w):
     ue = u_hi.double() + u_lo.double() / 2048
     we = (w_hi.double() + w_lo.double() / 2048) * inv
     out = torch.empty((12, cols // 128, rows, 128), device=dev)
-    _lib.check(lib.spb_wino_gemm(_lib.ptr(u_hi), _lib.ptr(u_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(out), rows, cols, inv, _lib.current_stream()))
+    _lib.check(lib.spb_wino_gemm(_lib.ptr(u_hi), _lib.ptr(u_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(out), rows, cols, inv, 0, _lib.current_stream()))
     m = torch.einsum("prk,pck->prc", ue, we.view(24, cols, 512)).view(6, 4, rows, cols)
     ref = torch.stack([m[:, 0] + m[:, 1] + m[:, 2], m[:, 1] - m[:, 2] - m[:, 3]], 1).reshape(12, rows, cols)
     got = out.permute(0, 2, 1, 3).reshape(12, rows, cols)

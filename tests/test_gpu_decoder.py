@@ -22,7 +22,8 @@ def lib():
     return _lib.load()
 
 
-def test_wino_gemm_row_transform(lib):
+@pytest.mark.parametrize("fine", [0, 1])
+def test_wino_gemm_row_transform(lib, fine):
     """The product path's gate GEMMs: 24 per-position GEMMs (K = 512) whose epilogue folds the four
     row positions of a Winograd F(2x4,3x3) tile into the two row-transformed planes."""
     from scanpaths_b200 import _lib
@@ -39,7 +40,7 @@ def test_wino_gemm_row_transform(lib):
     w_hi, w_lo, inv = split_pair(w)
     out = torch.full((12, cols // 128, rows, 128), float("nan"), device=dev)
     _lib.check(lib.spb_wino_gemm(_lib.ptr(u_hi), _lib.ptr(u_lo), _lib.ptr(w_hi), _lib.ptr(w_lo), _lib.ptr(out), rows,
-                                 cols, inv, _lib.current_stream()), "spb_wino_gemm")
+                                 cols, inv, fine, _lib.current_stream()), "spb_wino_gemm")
     m = torch.einsum("prk,pck->prc", u.double(), w.double().view(24, cols, 512)).view(6, 4, rows, cols)   # [j][i]
     ref = torch.stack([m[:, 0] + m[:, 1] + m[:, 2], m[:, 1] - m[:, 2] - m[:, 3]], 1).reshape(12, rows, cols)
     got = out.permute(0, 2, 1, 3).reshape(12, rows, cols)
@@ -133,13 +134,13 @@ def _decode_case(name, use_tc, golden_dir, steps=None):
 
 
 @pytest.mark.parametrize("name", ["coco", "air", "osie"])
-@pytest.mark.parametrize("use_tc", [0, 1, 2, 3])
+@pytest.mark.parametrize("use_tc", [0, 1, 2, 3, 4])
 def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
     """use_tc: 0 = SIMT fp32 check kernels with the explicit 5x5 layer (an independent route to the
     same numbers), 1 = the product path (tcgen05: Winograd h-gate GEMMs, direct x-gate GEMM, composed head),
     2 = direct 3x3 implicit GEMM for both, 3 = Winograd for both.  All T = 16 steps of every variant."""
     worst = _decode_case(name, use_tc, golden_dir)
-    print(name, ["simt", "product", "tc-direct", "tc-winograd"][use_tc], worst)
+    print(name, ["simt", "product", "tc-direct", "tc-winograd", "tc-winograd-fine-x"][use_tc], worst)
     _record_margin("golden_%s_mode%d" % (name, use_tc), worst)
     for k, v in worst.items():
         if k.endswith("ref_f32_prob"):
@@ -258,8 +259,10 @@ def test_acc_trunc_fix_validity_range(lib):
     mixed = BA.measure_acc_trunc_bias(dev)
     mixed2 = BA.measure_acc_trunc_bias(dev, seed=777)
     signed = BA.measure_acc_trunc_bias(dev, one_signed=True)
-    print("accumulator bias: mixed-sign %.3e / %.3e, one-signed %.3e" % (mixed, mixed2, signed))
-    _record_margin("acc_trunc_bias", {"mixed": mixed, "mixed_other_seed": mixed2, "one_signed": signed})
+    fine = BA.measure_acc_trunc_bias(dev, fine=True)
+    print("accumulator bias: mixed-sign %.3e / %.3e, one-signed %.3e; 8-k-step accumulators %.3e" % (mixed, mixed2, signed, fine))
+    _record_margin("acc_trunc_bias", {"mixed": mixed, "mixed_other_seed": mixed2, "one_signed": signed, "fine_8_steps": fine})
+    assert 0.0 <= fine < mixed
     assert 3.5e-7 < mixed < 8e-7 and abs(mixed - mixed2) < 5e-8, (mixed, mixed2)
     assert 1e-6 < signed < 5e-6, signed
     fix = BA.calibrate_acc_trunc_fix(dev)
