@@ -15,6 +15,7 @@
 // themselves off), so the four groups never diverge.
 // Strings longer than a panel carry the panel's last column in a per-group global workspace.
 #include <math.h>
+#include <stdlib.h>
 
 #include "score_common.cuh"
 
@@ -22,7 +23,7 @@ namespace spb {
 
 constexpr int kG = 8;                     // lanes per pair
 constexpr int kPairsPerWarp = 32 / kG;
-constexpr int kG8Warps = 4;               // warps per block -> 16 pairs per block
+constexpr int kG8Warps = 4;               // warps per block, at most (16 pairs per block); SPB_SCORE_WARPS=1|2|4 picks the launch size
 constexpr int kWdC = 16;                  // with-duration columns per lane, at most (the warp uses ceil(m / 8), rounded up to 4/8/12/16)
 constexpr int kWdPanel = kG * kWdC;       // 128
 
@@ -307,8 +308,9 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
     uint8_t *ar = base + L.ar, *ac = base + L.ac, *br = base + L.br, *bc = base + L.bc;
     uint8_t *awr = base + L.awr, *awc = base + L.awc, *bwr = base + L.bwr, *bwc = base + L.bwc;
 
-    const int64_t gwarp = (int64_t)blockIdx.x * kG8Warps + wib;
-    const int64_t ngroups = (int64_t)gridDim.x * kG8Warps * kPairsPerWarp;
+    const int wpb = blockDim.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t ngroups = (int64_t)gridDim.x * wpb * kPairsPerWarp;
     double *bnd = workspace ? workspace + (gwarp * kPairsPerWarp + sub) * ws_per_group : nullptr;
     const int xbin = cfg.sm.Xbin;
     const unsigned gshift = (unsigned)(sub * kG);
@@ -432,6 +434,8 @@ score_pairs_g8_kernel(spb_path_pack A, spb_path_pack B, const int32_t *__restric
     }
 }
 
+static int g_score_warps = kG8Warps;
+
 int score_pairs_g8(const spb_path_pack &A, const spb_path_pack &B, const int32_t *pair_h, const int32_t *pair_s,
                    int64_t n_pairs, const spb_score_cfg &cfg, double *scores, void *workspace, int64_t workspace_bytes,
                    int32_t *err, cudaStream_t stream, int *handled) {
@@ -439,17 +443,27 @@ int score_pairs_g8(const spb_path_pack &A, const spb_path_pack &B, const int32_t
     if (cfg.sm.GapValue != 0.0 || B.lmax > kG * 4) return SPB_OK;
     const PairLayout L = make_layout(A.lmax, B.lmax);
     const int ntab_bytes = (cfg.sm.Xbin * cfg.sm.Ybin * 8 + 15) & ~15;
-    const size_t smem = (size_t)ntab_bytes + (size_t)L.bytes * kG8Warps * kPairsPerWarp;
-    if (smem > 227 * 1024) return SPB_OK;
+    // warps per block: 4 by default.  One-warp blocks (21 KB of shared memory, 5 K registers) are small enough to sit
+    // next to a persistent GEMM CTA (193 KB, 54 K registers) on the same SM: with SPB_SCORE_WARPS=1 the pipeline's
+    // tail stream scores wave w in the issue slots the tensor-bound gate GEMMs of wave w+1 leave idle.
+    static int wpb_env = -1;
+    if (wpb_env < 0) {
+        const char *e = getenv("SPB_SCORE_WARPS");
+        wpb_env = e ? atoi(e) : 0;
+        if (wpb_env != 1 && wpb_env != 2 && wpb_env != 4) wpb_env = 0;
+    }
+    int wpb = wpb_env ? wpb_env : g_score_warps;
+    if ((size_t)ntab_bytes + (size_t)L.bytes * wpb * kPairsPerWarp > 227 * 1024) return SPB_OK;
+    const size_t smem = (size_t)ntab_bytes + (size_t)L.bytes * wpb * kPairsPerWarp;
     const int lc = B.lmax <= kG * 2 ? 2 : 4;
     auto kern = lc == 2 ? score_pairs_g8_kernel<2> : score_pairs_g8_kernel<4>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kG8Warps * 32, smem));
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;                                    // <= 64 groups per SM (workspace sizing)
+    if (per_sm * wpb > 16) per_sm = 16 / wpb;                     // <= 64 groups per SM (workspace sizing)
     int64_t blocks = (int64_t)num_sms() * per_sm;                  // persistent grid, whole waves
-    const int64_t per_block = kG8Warps * kPairsPerWarp;
+    const int64_t per_block = wpb * kPairsPerWarp;
     const int64_t need = (n_pairs + per_block - 1) / per_block;
     if (blocks > need) blocks = need;
     int64_t ws_per_group = 0;
@@ -458,7 +472,7 @@ int score_pairs_g8(const spb_path_pack &A, const spb_path_pack &B, const int32_t
         ws_per_group &= ~(int64_t)1;
     }
     prof_begin(kTagScore, stream);
-    kern<<<(unsigned)blocks, kG8Warps * 32, smem, stream>>>(A, B, pair_h, pair_s, n_pairs, cfg, scores,
+    kern<<<(unsigned)blocks, wpb * 32, smem, stream>>>(A, B, pair_h, pair_s, n_pairs, cfg, scores,
                                                             ws_per_group > 0 ? (double *)workspace : nullptr, ws_per_group,
                                                             err);
     SPB_LAUNCH_CHECK();
