@@ -141,3 +141,37 @@ def test_pipeline_ragged_subject_counts_and_new_humans():
     fresh.set_humans(hx2, hl2)
     ref = fresh.run(vf.cuda(), keep_scores=True)
     assert torch.equal(again["scores"], ref["scores"]) and again["scores"].shape == (1, K, N, 2, 4)
+
+
+def test_pipeline_overlap_and_checksums_bench_shape():
+    """Bench-shaped slice (768 images = 3 waves x 64 samples x 15 subjects, 737,280 pairs): the tail of wave w on
+    the side stream under the decode of wave w+1 gives bit-identical results to the single-stream order, pinned
+    host input equals device input, and the reduced table is consistent with the device accumulators
+    (a checksum of checksums: sum over groups of the table's SED / STDE means x S == the accumulated sums)."""
+    from scanpaths_b200.pipeline import ScanpathPipeline
+    from scanpaths_b200.weights import random_state_dict
+    from bench import synth_humans
+    dev = torch.device("cuda")
+    N, K, Sn, T = 768, 64, 15, 16
+    g = torch.Generator(device=dev).manual_seed(3)
+    vf = torch.randn((N, 512, 30, 40), generator=g, device=dev).clamp_min_(0)
+    hx, hl = synth_humans(N, Sn, 9)
+    outs = []
+    for overlap, host in ((True, False), (False, False), (True, True)):
+        pipe = ScanpathPipeline(random_state_dict("OSIE", 0), "OSIE", T, K, 1, dev, 256, seed=5, overlap_tail=overlap)
+        pipe.set_humans(hx, hl)
+        src = vf.cpu().pin_memory() if host else vf
+        o = pipe.run(src, valid_min_len=0)
+        torch.cuda.synchronize()
+        outs.append({k: o[k].clone() for k in ("table", "reward", "group_valid", "acc")})
+        del pipe
+    for other in outs[1:]:
+        for k in ("table", "reward", "group_valid", "acc"):
+            assert torch.equal(torch.nan_to_num(outs[0][k].double(), nan=-1.0), torch.nan_to_num(other[k].double(), nan=-1.0)), k
+    tab, acc = outs[0]["table"][0].double(), outs[0]["acc"][0]
+    assert acc[12].item() == N * K * Sn and acc[13].item() == N * K and acc[14].item() == N * K
+    for slot, a in ((5, 1), (6, 0), (7, 2), (8, 3)):                  # table means x S vs accumulated sums (f32 rows)
+        assert (tab[..., slot].sum() * Sn).item() == pytest.approx(acc[a].item(), rel=2e-6)
+    assert tab[..., 9].sum().item() == pytest.approx(acc[8].item(), rel=1e-6)       # SED best
+    assert tab[..., 10].sum().item() == pytest.approx(acc[9].item(), rel=1e-6)      # STDE best
+    assert torch.isfinite(outs[0]["reward"]).all() and (outs[0]["reward"] > 0).all()
