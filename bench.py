@@ -280,13 +280,13 @@ class ClockSampler:
 class Workload:
     """One task-shaped workload resident on one GPU: pipeline + synthetic features / humans."""
 
-    def __init__(self, args, task, n_local, S, dev, rank, vf_dev=None):
+    def __init__(self, args, task, n_local, S, dev, rank, vf_dev=None, calibrated=True):
         import torch
         from scanpaths_b200.pipeline import ScanpathPipeline
         from scanpaths_b200.weights import random_state_dict
         self.task, self.N, self.K, self.S, self.dev, self.args = task, n_local, args.samples, S, dev, args
-        self.pipe = ScanpathPipeline(random_state_dict(task, 0), task, T_STEPS, self.K, 1, dev, args.wave,
-                                     seed=1234 + rank)
+        self.pipe = ScanpathPipeline(random_state_dict(task, 0, calibrated=calibrated), task, T_STEPS, self.K, 1, dev,
+                                     args.wave, seed=1234 + rank)
         self.heads = self.pipe.decoder.heads
         gen = torch.Generator(device=dev).manual_seed(1000 + rank)
         if vf_dev is None:                                # features relu(N(0,1)) generated on the device in chunks
@@ -588,6 +588,35 @@ def human_eval_record(args, dev, peaks, cpu):
     return rec
 
 
+def stress_record(args, dev, vf_dev, barrier):
+    """SURVEY 8d's long-string stress case: RAW random-init weights (no bias calibration) -- the model almost never
+    stops (16 fixations per scanpath) and draws durations around exp(N(0, 1)) s, so the with-duration strings of
+    the predictions are ~500 symbols instead of ~50 and every pair takes the warp-per-pair multi-panel kernel.
+    One wave of images; decode + sample + score like the headline."""
+    import torch
+    n = min(args.wave, args.images)
+    w = Workload(args, "OSIE", n, args.subjects, dev, 0, vf_dev=vf_dev[:n], calibrated=False)
+    w.step()
+    steps = 2
+    ms, out = timed_steps(w.step, steps, barrier, dev)
+    from scanpaths_b200.pipeline import ScanpathPipeline
+    m, _ = ScanpathPipeline.metrics(out)
+    res = w.pipe.run(w.vf_dev, keep_paths=True)
+    smp = res["paths"][0][3]
+    from scanpaths_b200 import scoring as SC
+    pp = SC.prep_paths(smp["xyd"], smp["len"], w.pipe.cfg)
+    rec = {"workload": "OSIE-shaped, raw random-init weights: %d images x %d samples x %d subjects" % (n, w.K, w.S),
+           "value": n * w.K * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+           "pred_fixations_mean": float(smp["len"].float().mean()),
+           "pred_wd_string_mean": float(pp.nwd.float().mean()), "pred_wd_string_max": int(pp.nwd.max()),
+           "human_wd_string_mean": float(w.pipe.humans.nwd.float().mean()),
+           "scores": {"ScanMatch_wd": m["ScanMatch"]["with duration"], "ScanMatch_wod": m["ScanMatch"]["w/o duration"],
+                      "SED": m["VAME"]["SED"], "STDE": m["VAME"]["STDE"]}}
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
 def extra_task_record(args, task, dev, lib, peaks, cpu, vf_dev, do_e2e, barrier):
     """A task-shaped 1-GPU record (AiR: two streams / two heads -> 2K samples per image; COCO: per-image 5x5 weights)."""
     import torch
@@ -726,7 +755,8 @@ def main():
                          ("COCO_Search18", lambda: extra_task_record(args, "COCO_Search18", dev, lib, peaks,
                                                                      cpu.get("COCO_Search18"), vf_dev, False, barrier)),
                          ("scst_reward_step", lambda: scst_record(args, dev, lib, cpu.get("scst"))),
-                         ("human_evaluation", lambda: human_eval_record(args, dev, peaks, cpu.get("human_eval")))):
+                         ("human_evaluation", lambda: human_eval_record(args, dev, peaks, cpu.get("human_eval"))),
+                         ("raw_random_init_stress", lambda: stress_record(args, dev, vf_dev, barrier))):
             try:
                 extra[name] = fn()
             except Exception as e:                        # an extra record must never cost the headline line

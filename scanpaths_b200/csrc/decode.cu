@@ -999,7 +999,6 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.vfmean = (float *)take(N * kHW * 4);
     w.xg = (float *)take(N * kHW * kGateCols * 4);
     w.c = (float *)take(N * kHW * kE * 4);
-    w.acc = (float *)take(N * kHW * kGateCols * 4);
     w.feat = (float *)take(N * kHW * HD * kE * 4);
     w.z23 = w.feat;
     w.gemm_rows = (N + 239) / 240 * 240;
@@ -1024,9 +1023,14 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.se_mem = (float *)take(N * S * kE * 4);
     w.drt_pre = (float *)take(N * HD * 48 * 4);
     w.rows_pad = (N * kTilesPerImg + 127) / 128 * 128;
+    // the direct routes' gate pre-activations (acc, 9.8 MB per image) and the Winograd routes' operands and planes
+    // (u, wm: 22 MB per image) are never live in the same decode: one region serves both
+    const int64_t wino_start = o;
     w.u_hi = (__half *)take(kWinoPos * w.rows_pad * kE * 2);
     w.u_lo = (__half *)take(kWinoPos * w.rows_pad * kE * 2);
     w.wm = (float *)take((kWinoPos / 2) * w.rows_pad * (int64_t)kGateCols * 4);
+    w.acc = base ? (float *)((char *)base + wino_start) : nullptr;
+    if (o - wino_start < N * kHW * kGateCols * 4) o = wino_start + ((N * kHW * kGateCols * 4 + 1023) & ~(int64_t)1023);
     w.bytes = o;
     return w;
 }
