@@ -375,35 +375,46 @@ constexpr int kWinoPos = 24;        // position p = 4j + i (i: F(2,3) row positi
 
 // U[p][n*150 + tile][ci] = (B2^T d B4)[i][j].  One block per (image, tile row), thread = 2 channels, walking the 10
 // tiles of the row: the row half B2^T of the transform is applied to each pixel column once and the two columns a
-// tile shares with its left neighbour stay in registers (16 new pixel loads per tile instead of 24), the loads of
-// the next tile are issued before this tile's column transform and its 48 stores, and a block writes 10 KB
-// contiguous per position plane.  HBM-bound: 2.5 MB read + 7.2 MB written per image.
+// tile shares with its left neighbour stay in registers (16 new pixels per tile instead of 24).
+// The 16 new pixels of a tile (4 rows x 4 columns x 512 channels, hi and lo: 32 KB) are staged in shared memory
+// by cp.async (16-byte chunks, L2 -> shared, zero-filled outside the image = the convolution's padding), three
+// tiles deep: two tiles of loads are in flight per block (128 KB per SM) while one is transformed, at no
+// register cost -- the register-prefetch version (one tile ahead, 128 registers, 16 warps per SM) was
+// latency-bound at 0.78 of the HBM rate alone and 0.65 inside the step.
+// A block writes 10 KB contiguous per position plane.  HBM-bound: 2.5 MB read + 7.2 MB written per image.
+constexpr int kWinStages = 3;
+constexpr int kWinStageHalfs = 4 * 4 * kE;                  // one of (hi, lo): 4 rows x 4 pixel columns x 512 channels
+constexpr int kWinSmemBytes = kWinStages * 2 * kWinStageHalfs * 2;   // 96 KB: two blocks per SM
+
 __global__ void __launch_bounds__(256, 2)
 wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_lo, __half *__restrict__ u_hi,
                   __half *__restrict__ u_lo, int64_t rows_pad) {
+    extern __shared__ __align__(16) unsigned char win_smem[];
     const int64_t n = blockIdx.x / kTilesY;
     const int ty = (int)(blockIdx.x - n * kTilesY);
     const int c0 = threadIdx.x * 2;
-    // rows 2ty-1 .. 2ty+2 of the image: clamped address + validity flag (out-of-image rows are the zero padding)
-    int64_t row_off[4];
-    bool row_in[4];
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(win_smem);
+    // stage of tile tx: [part: hi, lo][row a][column b][512 channels] halfs; thread copies 16-byte chunks
+    // k = tid, tid + 256, ...: k -> (part = k >> 10, pixel = (k >> 6) & 15, chunk of 8 channels = k & 63)
+    auto issue = [&](int tx) {
+        const uint32_t dst0 = smem0 + (uint32_t)(tx % kWinStages) * (2 * kWinStageHalfs * 2);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int yy = 2 * ty - 1 + a;
-        row_in[a] = yy >= 0 && yy < kH;
-        row_off[a] = ((n * kH + min(max(yy, 0), kH - 1)) * kW) * (int64_t)kE + c0;
-    }
-    uint32_t rh[4][4], rl[4][4];                     // raw (hi, lo) pairs of the 4 new pixel columns of a tile
-    auto issue = [&](int tx) {                       // columns 4tx+1 .. 4tx+4 (the last one may be x = 40: padding)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int xx = min(4 * tx + 1 + b, kW - 1);
-                rh[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_hi + row_off[a] + (int64_t)xx * kE));
-                rl[a][b] = __ldg(reinterpret_cast<const uint32_t *>(h_lo + row_off[a] + (int64_t)xx * kE));
-            }
+        for (int r = 0; r < 8; ++r) {
+            const int k = threadIdx.x + r * 256;
+            const int part = k >> 10, pix = (k >> 6) & 15, ch = (k & 63) * 8;
+            const int yy = 2 * ty - 1 + (pix >> 2), xx = 4 * tx + 1 + (pix & 3);
+            const bool in = yy >= 0 && yy < kH && xx < kW;
+            const __half *src = (part ? h_lo : h_hi) +
+                                ((n * kH + min(max(yy, 0), kH - 1)) * kW + min(xx, kW - 1)) * (int64_t)kE + ch;
+            const uint32_t dst = dst0 + (uint32_t)((part * 16 + pix) * kE + ch) * 2u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
+        }
     };
+#pragma unroll
+    for (int tx = 0; tx < kWinStages - 1; ++tx) {
+        issue(tx);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     float u[4][6][2];                                // row-transformed columns of the current tile
     // tile 0: column x = -1 is padding, column x = 0 is loaded here
 #pragma unroll
@@ -412,12 +423,15 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
         float d[4][2];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const uint32_t vh = __ldg(reinterpret_cast<const uint32_t *>(h_hi + row_off[a]));
-            const uint32_t vl = __ldg(reinterpret_cast<const uint32_t *>(h_lo + row_off[a]));
+            const int yy = 2 * ty - 1 + a;
+            const bool in = yy >= 0 && yy < kH;
+            const int64_t off = ((n * kH + min(max(yy, 0), kH - 1)) * kW) * (int64_t)kE + c0;
+            const uint32_t vh = __ldg(reinterpret_cast<const uint32_t *>(h_hi + off));
+            const uint32_t vl = __ldg(reinterpret_cast<const uint32_t *>(h_lo + off));
             const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&vh));
             const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&vl));
-            d[a][0] = row_in[a] ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
-            d[a][1] = row_in[a] ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
+            d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
+            d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -427,25 +441,30 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
             u[3][5][e] = d[1][e] - d[3][e];
         }
     }
-    issue(0);
     for (int tx = 0; tx < kTilesX; ++tx) {
+        // tile tx has landed for every thread, and every thread is done with the stage tile tx + 2 will overwrite
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWinStages - 2) : "memory");
+        __syncthreads();
+        if (tx + kWinStages - 1 < kTilesX) issue(tx + kWinStages - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         // shift: the previous tile's last two columns are this tile's first two
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int e = 0; e < 2; ++e) { u[i][0][e] = u[i][4][e]; u[i][1][e] = u[i][5][e]; }
-        // row transform of the 4 new columns
+        // row transform of the 4 new columns (zero-filled outside the image)
+        const unsigned char *st = win_smem + (size_t)(tx % kWinStages) * (2 * kWinStageHalfs * 2);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const bool col_in = 4 * tx + 1 + b < kW;
             float d[4][2];
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&rh[a][b]));
-                const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&rl[a][b]));
-                const bool in = row_in[a] && col_in;
-                d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
-                d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
+                const uint32_t vh = *reinterpret_cast<const uint32_t *>(st + ((a * 4 + b) * kE + c0) * 2);
+                const uint32_t vl = *reinterpret_cast<const uint32_t *>(st + ((16 + a * 4 + b) * kE + c0) * 2);
+                const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&vh));
+                const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&vl));
+                d[a][0] = fa.x + fb.x * (1.0f / kLoScale);
+                d[a][1] = fa.y + fb.y * (1.0f / kLoScale);
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -455,7 +474,6 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
                 u[3][2 + b][e] = d[1][e] - d[3][e];
             }
         }
-        if (tx + 1 < kTilesX) issue(tx + 1);          // next tile's loads fly during this tile's stores
         const int64_t nt = n * kTilesPerImg + ty * kTilesX + tx;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1169,6 +1187,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     const bool wino_x = io->use_tensor_cores == 3 || io->use_tensor_cores == 4;
     const bool wino_x_fine = io->use_tensor_cores == 4;
     const int64_t NP = N * kHW;
+    if (wino) SPB_CUDA(cudaFuncSetAttribute(wino_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));
 
     // ---- once per image: operand layout, loop-invariant x-convolutions, zero state
     prof_begin(kTagPrep, s);
@@ -1179,7 +1198,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     prof_begin(kTagConvX, s);
     if (wino_x) {
         // the loop-invariant x-gate convolution through the same Winograd F(2x4,3x3) kernels as the h-gates
-        wino_input_kernel<<<(unsigned)(N * kTilesY), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
+        wino_input_kernel<<<(unsigned)(N * kTilesY), 256, kWinSmemBytes, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, ws.rows_pad);
         SPB_LAUNCH_CHECK();
         SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->wwx_hi, (const __half *)w->wwx_lo, ws.wm, ws.rows_pad,
                              kGateCols, w->inv_scale_wx, s, wino_x_fine));
@@ -1256,7 +1275,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             // on tcgen05, output transform folded into the ConvLSTM cell.  h(0) = 0 -> nothing to multiply.
             if (t > 0) {
                 prof_begin(kTagWinoIn, s);
-                wino_input_kernel<<<(unsigned)(N * kTilesY), 256, 0, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
+                wino_input_kernel<<<(unsigned)(N * kTilesY), 256, kWinSmemBytes, s>>>(ws.h_hi[cur], ws.h_lo[cur], ws.u_hi, ws.u_lo,
                                                                              ws.rows_pad);
                 SPB_LAUNCH_CHECK();
                 prof_end(s);
