@@ -889,37 +889,52 @@ init_spatial_feat_kernel(const float *__restrict__ att, const float *__restrict_
 }
 
 // semantic feedback feature (get_channel_semantic :232-236, :362): relu(mean_p(map[p] vf[c,p])).
-// One warp per (image, channel); `maps` holds S maps per image with stride map_stride between
-// streams and image_stride between images (att: S identical copies via stride 0).
+// One warp per (image, channel), a block = 8 channels of one image; `maps` holds S maps per image with stride
+// map_stride between streams and image_stride between images (att: S identical copies via stride 0).
+// HBM-bound (re-reads the wave's feature maps, 2.46 MB per image): every lane issues its 10 float4 loads of the
+// feature row before anything else (160 B in flight per lane), the image's map(s) are staged once per block in
+// shared memory instead of being re-read through L1 by each of the 8 warps.
 __global__ void __launch_bounds__(256)
 semantic_feat_kernel(const float *__restrict__ vf, const float *__restrict__ maps, int64_t image_stride,
                      int64_t stream_stride, int S, float *__restrict__ se_feat, __half *__restrict__ sf_hi,
                      __half *__restrict__ sf_lo, int64_t n_images) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (warp >= n_images * kE) return;
-    const int64_t n = warp / kE;
-    const int c = (int)(warp - n * kE);
+    constexpr int kRow4 = kHW / 4;                           // 300 float4 per feature row / map
+    constexpr int kPer = (kRow4 + 31) / 32;                  // 10 per lane
+    __shared__ float4 smap[2][kRow4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t n = blockIdx.x / (kE / 8);
+    const int c = (int)(blockIdx.x - n * (kE / 8)) * 8 + wib;
     const float4 *row = reinterpret_cast<const float4 *>(vf + (n * kE + c) * kHW);
-    float s[2] = {0.0f, 0.0f};
-    for (int p4 = lane; p4 < kHW / 4; p4 += 32) {
-        const float4 v = row[p4];
-        for (int st = 0; st < S; ++st) {
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (maps) m = *reinterpret_cast<const float4 *>(maps + n * image_stride + st * stream_stride + 4 * p4);
-            s[st] = fmaf(v.x, m.x, s[st]); s[st] = fmaf(v.y, m.y, s[st]);
-            s[st] = fmaf(v.z, m.z, s[st]); s[st] = fmaf(v.w, m.w, s[st]);
-        }
+    float4 v[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int p4 = lane + 32 * q;
+        v[q] = p4 < kRow4 ? __ldg(row + p4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    for (int i = threadIdx.x; i < S * kRow4; i += blockDim.x) {
+        const int st = i / kRow4, p4 = i - st * kRow4;
+        smap[st][p4] = maps ? *reinterpret_cast<const float4 *>(maps + n * image_stride + st * stream_stride + 4 * p4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
     for (int st = 0; st < S; ++st) {
-        float a = s[st];
+        float a = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int p4 = lane + 32 * q;
+            if (p4 < kRow4) {
+                const float4 m = smap[st][p4];
+                a = fmaf(v[q].x, m.x, a); a = fmaf(v[q].y, m.y, a);
+                a = fmaf(v[q].z, m.z, a); a = fmaf(v[q].w, m.w, a);
+            }
+        }
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) {
-            const float v = fmaxf(a / (float)kHW, 0.0f);
-            se_feat[(n * S + st) * kE + c] = v;
+            const float r = fmaxf(a / (float)kHW, 0.0f);
+            se_feat[(n * S + st) * kE + c] = r;
             if (sf_hi) {                                  // operand of the tensor-core semantic_embed GEMM
                 __half hh, hl;
-                split_one(v, hh, hl);
+                split_one(r, hh, hl);
                 sf_hi[(n * S + st) * kE + c] = hh; sf_lo[(n * S + st) * kE + c] = hl;
             }
         }
@@ -1245,7 +1260,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     SPB_CUDA(cudaMemsetAsync(ws.sm_lo, 0, (size_t)S * ws.gemm_rows * kE * 2, s));
     SPB_CUDA(cudaMemsetAsync(ws.sf_hi, 0, (size_t)ws.gemm_rows2 * kE * 2, s));
     SPB_CUDA(cudaMemsetAsync(ws.sf_lo, 0, (size_t)ws.gemm_rows2 * kE * 2, s));
-    semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(io->d_vf, io->d_att, kHW, 0, S,
+    semantic_feat_kernel<<<(unsigned)(N * (kE / 8)), 256, 0, s>>>(io->d_vf, io->d_att, kHW, 0, S,
                                                                               ws.se_feat, tc ? ws.sf_hi : nullptr, ws.sf_lo, N);
     SPB_LAUNCH_CHECK();
     prof_begin(kTagFeedback, s);
@@ -1362,7 +1377,7 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
             prof_begin(kTagFeedback, s);
             // semantic feedback from this step's action map(s): map of (head hd, image n) lives at
             // d_action_map[((hd*N + n)*T + t)*1200]
-            semantic_feat_kernel<<<(unsigned)((N * kE * 32 + 255) / 256), 256, 0, s>>>(
+            semantic_feat_kernel<<<(unsigned)(N * (kE / 8)), 256, 0, s>>>(
                 io->d_vf, io->d_action_map + (int64_t)t * kHW, (int64_t)T * kHW, N * (int64_t)T * kHW, S, ws.se_feat,
                 tc ? ws.sf_hi : nullptr, ws.sf_lo, N);
             SPB_LAUNCH_CHECK();
