@@ -305,6 +305,9 @@ typedef struct spb_decoder_weights {
     const void *ww_hi, *ww_lo;       /* fp16 [24*2048, 512] Winograd F(2x4,3x3)-transformed lstm.*_h: G2 g G4^T,     */
                                      /*   position-major, position = 4*(column position j) + (row position i)   */
     const void *wwx_hi, *wwx_lo;     /* the same for lstm.*_x (the loop-invariant x-gate convolution)              */
+    const void *wwx2_hi, *wwx2_lo;   /* fp16 [16*2048, 512] Winograd F(2x2,3x3)-transformed lstm.*_x: G2 g G2^T,   */
+                                     /*   position = 4*(column position j) + (row position i): the product path's  */
+                                     /*   x-gate convolution                                                       */
     const float *bias_gate;          /* [2048]  b_x + b_h + sum over streams b_m         */
     const float *bias_p;             /* [n_weight_sets*512]                              */
     const float *wm;                 /* [n_streams*3*512*9, 512] rank-1 gate weights:    */
@@ -331,7 +334,8 @@ typedef struct spb_decoder_weights {
     const float *w_eff_spatial;      /* [1200] spatial_att: spatial_attention correlated with spatial_lists */
     const float *u_semantic;         /* [512]  semantic_att: semantic_lists^T semantic_attention            */
     float b2, b3, bd1, bd2_mu, bd2_sigma;
-    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_wx, inv_scale_23, inv_scale_m, inv_scale_se;   /* 1 / (power-of-two scale of the fp16 weight pairs) */
+    float inv_scale_x, inv_scale_h, inv_scale_p, inv_scale_w, inv_scale_wx, inv_scale_23, inv_scale_m, inv_scale_se,
+          inv_scale_wx2;             /* 1 / (power-of-two scale of the fp16 weight pairs) */
     int32_t n_streams;               /* 1 (OSIE, COCO) or 2 (AiR pos / neg)             */
     int32_t n_heads;                 /* 1 or 2 (AiR good / poor)                        */
     int32_t n_weight_sets;           /* 1, 2 (AiR: True, False) or 18 (COCO tasks)      */
@@ -340,9 +344,10 @@ typedef struct spb_decoder_weights {
 
 typedef struct spb_decoder_io {
     int32_t n_images, steps;
-    int32_t use_tensor_cores;        /* 1 (product path): tcgen05, Winograd F(2x4,3x3) GEMMs for the h-gates, direct */
-                                     /*   implicit GEMM for the loop-invariant x-gates, composed head;                */
-                                     /* 2: direct 3x3 implicit GEMM for both; 3: Winograd for both;                   */
+    int32_t use_tensor_cores;        /* 1 (product path): tcgen05, Winograd F(2x4,3x3) GEMMs for the h-gates,        */
+                                     /*   Winograd F(2x2,3x3) for the loop-invariant x-gates, composed head;          */
+                                     /* 2: direct 3x3 implicit GEMM for both; 3: Winograd F(2x4) for both (4: with    */
+                                     /*   8-k-step accumulators for the x-gates); 5: F(2x4) h-gates + direct x-gates; */
                                      /* 0: SIMT fp32 check kernels with the explicit 5x5 layer                        */
     int32_t reserved;
     const float *d_vf;               /* [N, 512, 30, 40] visual_feature (NCHW, as the encoder emits it) */

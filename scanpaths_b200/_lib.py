@@ -73,11 +73,12 @@ SYMBOLS = {
 
 class DecoderWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("wx_hi", "wx_lo", "wh_hi", "wh_lo", "wp_hi", "wp_lo", "ww_hi", "ww_lo", "wwx_hi", "wwx_lo", "bias_gate", "bias_p", "wm", "wm_hi", "wm_lo", "w2", "w3", "wd1",
+                ("wx_hi", "wx_lo", "wh_hi", "wh_lo", "wp_hi", "wp_lo", "ww_hi", "ww_lo", "wwx_hi", "wwx_lo", "wwx2_hi", "wwx2_lo", "bias_gate", "bias_p", "wm", "wm_hi", "wm_lo", "w2", "w3", "wd1",
                  "wd2", "w_spatial_embed", "b_spatial_embed", "w_semantic_embed", "b_semantic_embed", "wse_hi", "wse_lo",
                  "w23_hi", "w23_lo", "b23_eff", "wd_eff", "bd_eff", "w_eff_spatial", "u_semantic")] + \
                [(n, C.c_float) for n in ("b2", "b3", "bd1", "bd2_mu", "bd2_sigma", "inv_scale_x", "inv_scale_h",
-                                         "inv_scale_p", "inv_scale_w", "inv_scale_wx", "inv_scale_23", "inv_scale_m", "inv_scale_se")] + \
+                                         "inv_scale_p", "inv_scale_w", "inv_scale_wx", "inv_scale_23", "inv_scale_m", "inv_scale_se",
+                                         "inv_scale_wx2")] + \
                [(n, C.c_int32) for n in ("n_streams", "n_heads", "n_weight_sets", "reserved")]
 
 

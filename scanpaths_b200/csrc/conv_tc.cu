@@ -728,10 +728,16 @@ int conv_gemm_tc(const ConvGemmArgs &a_in, cudaStream_t s) {
 // Winograd F(2x4,3x3) gate GEMMs + row output transform (wino_gemm_tc_kernel).
 //   u  [24][rows_pad][512] fp16 pairs (hi + lo/2^11), position p = 4j + i;  w [24 * cols][512] fp16 pairs;
 //   out [12][cols/128][rows_pad][128] fp32.  rows_pad % 128 == 0, cols % 128 == 0.
+//   pos_j = 4: the same kernel on the 16 positions of F(2x2,3x3) (u [16][..], w [16 * cols][..], out [8][..]) --
+//   the row positions i and their fold in the epilogue are those of F(2,3) either way.
 int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
-                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain) {
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain, int pos_j) {
     using namespace tc;
-    constexpr int kPos = wg::kPosI * wg::kPosJ;
+    if (pos_j != wg::kPosJ && pos_j != 4) {
+        set_error("wino_gemm_tc: 6 (F(2x4)) or 4 (F(2x2)) column positions");
+        return SPB_ERR_ARG;
+    }
+    const int kPos = wg::kPosI * pos_j;
     if (rows_pad <= 0 || rows_pad % wg::kTileRows != 0 || cols <= 0 || cols % kTileCh != 0 || ((uintptr_t)out & 15) != 0) {
         set_error("wino_gemm_tc: rows_pad must be a multiple of %d, cols of %d", wg::kTileRows, kTileCh);
         return SPB_ERR_ARG;
@@ -742,7 +748,7 @@ int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, con
     }
     const int nct = cols / kTileCh;
     const int64_t ntb = rows_pad / wg::kTileRows;
-    if ((int64_t)kPos * rows_pad > 0x7fffffff || wg::kPosJ * nct * ntb > 0x7fffffff) {
+    if ((int64_t)kPos * rows_pad > 0x7fffffff || pos_j * nct * ntb > 0x7fffffff) {
         set_error("wino_gemm_tc: too many rows");
         return SPB_ERR_ARG;
     }
@@ -765,7 +771,7 @@ int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, con
         set_error("wino_gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", rc);
         return SPB_ERR_CUDA;
     }
-    const int num_tiles = (int)(wg::kPosJ * nct * ntb);
+    const int num_tiles = (int)(pos_j * nct * ntb);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     if (fine_drain) {
         SPB_CUDA(cudaFuncSetAttribute(wino_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));

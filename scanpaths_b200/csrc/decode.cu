@@ -631,6 +631,138 @@ wino_output_kernel(const float *__restrict__ M, int64_t rows_pad, const float *_
 }
 
 // ---------------------------------------------------------------------------
+// Winograd F(2x2, 3x3) for the loop-invariant x-gate convolution of the product path: 16 multiplies per 4
+// outputs (direct: 36), through the same tcgen05 GEMM kernel as the h-gates (16 positions p = 4j + i, the row
+// positions i and their fold in the epilogue are F(2,3)'s either way).  Its error is the direct form's to within
+// 10 % (emulated with the truncating accumulator, scratch/wino_emul.py: 5.0e-7 of the convolution's rms against
+// 4.6e-7; F(2x4): 7.7e-7) -- it matters because the x-gates enter the pre-activations of all 16 steps.
+//   B2^T = [1 0 -1 0; 0 1 1 0; 0 -1 1 0; 0 1 0 -1],  A2^T = [1 1 1 0; 0 1 -1 -1]
+// Tiles: 15 x 20 per image; input patch rows 2ty-1 .. 2ty+2, columns 2tx-1 .. 2tx+2.  Images [n0, n0 + gridDim/15)
+// of the wave go through one call (half a wave at a time: the operands then fit the buffers of the h-gate GEMMs).
+// ---------------------------------------------------------------------------
+constexpr int kTiles22X = 20, kTiles22PerImg = kTilesY * kTiles22X, kWino22Pos = 16;
+
+__global__ void __launch_bounds__(256, 2)
+wino_input22_kernel(const __half *__restrict__ x_hi, const __half *__restrict__ x_lo, __half *__restrict__ u_hi,
+                    __half *__restrict__ u_lo, int64_t rows_pad, int64_t n0) {
+    const int64_t nl = blockIdx.x / kTilesY, n = n0 + nl;
+    const int ty = (int)(blockIdx.x - nl * kTilesY);
+    const int c0 = threadIdx.x * 2;
+    int64_t row_off[4];
+    bool row_in[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int yy = 2 * ty - 1 + a;
+        row_in[a] = yy >= 0 && yy < kH;
+        row_off[a] = ((n * kH + min(max(yy, 0), kH - 1)) * kW) * (int64_t)kE + c0;
+    }
+    uint32_t rh[4][2], rl[4][2];                     // raw (hi, lo) pairs of the 2 new pixel columns of a tile
+    auto issue = [&](int tx) {                       // columns 2tx+1, 2tx+2 (the last one may be x = 40: padding)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int xx = min(2 * tx + 1 + b, kW - 1);
+                rh[a][b] = __ldg(reinterpret_cast<const uint32_t *>(x_hi + row_off[a] + (int64_t)xx * kE));
+                rl[a][b] = __ldg(reinterpret_cast<const uint32_t *>(x_lo + row_off[a] + (int64_t)xx * kE));
+            }
+    };
+    auto rows_of = [&](uint32_t (&vh)[4], uint32_t (&vl)[4], bool col_in, float (&o)[4][2]) {   // B2^T down a column
+        float d[4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&vh[a]));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&vl[a]));
+            const bool in = row_in[a] && col_in;
+            d[a][0] = in ? fa.x + fb.x * (1.0f / kLoScale) : 0.0f;
+            d[a][1] = in ? fa.y + fb.y * (1.0f / kLoScale) : 0.0f;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            o[0][e] = d[0][e] - d[2][e];
+            o[1][e] = d[1][e] + d[2][e];
+            o[2][e] = d[2][e] - d[1][e];
+            o[3][e] = d[1][e] - d[3][e];
+        }
+    };
+    float u[4][4][2];                                // [column of the patch][row position i][element]
+    // tile 0: column x = -1 is padding, column x = 0 is loaded here
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[2][i][0] = u[2][i][1] = 0.0f;
+    {
+        uint32_t vh[4], vl[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            vh[a] = __ldg(reinterpret_cast<const uint32_t *>(x_hi + row_off[a]));
+            vl[a] = __ldg(reinterpret_cast<const uint32_t *>(x_lo + row_off[a]));
+        }
+        rows_of(vh, vl, true, u[3]);
+    }
+    issue(0);
+    for (int tx = 0; tx < kTiles22X; ++tx) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { u[0][i][e] = u[2][i][e]; u[1][i][e] = u[3][i][e]; }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            uint32_t vh[4], vl[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { vh[a] = rh[a][b]; vl[a] = rl[a][b]; }
+            rows_of(vh, vl, 2 * tx + 1 + b < kW, u[2 + b]);
+        }
+        if (tx + 1 < kTiles22X) issue(tx + 1);        // next tile's loads fly during this tile's stores
+        const int64_t nt = nl * kTiles22PerImg + ty * kTiles22X + tx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float t[4][2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                t[0][e] = u[0][i][e] - u[2][i][e];
+                t[1][e] = u[1][i][e] + u[2][i][e];
+                t[2][e] = u[2][i][e] - u[1][i][e];
+                t[3][e] = u[1][i][e] - u[3][i][e];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                __half hh[2], hl[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
+                const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
+                *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+                *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
+            }
+        }
+    }
+}
+
+// Column half of the F(2x2) output transform: xg[pix][col] = (t . A2)[r][ox] + bias[col] with t[r][j] = plane 2j + r
+// of the GEMM.  Block = (tile row, local image, 128-column tile), thread = gate column.
+__global__ void __launch_bounds__(128)
+wino_output22_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ bias, float *__restrict__ xg,
+                     int64_t n0) {
+    const int64_t nl = blockIdx.y, n = n0 + nl;
+    const int ty = blockIdx.x, ct = blockIdx.z;
+    const float b = bias[ct * 128 + threadIdx.x];
+#pragma unroll 2
+    for (int tx = 0; tx < kTiles22X; ++tx) {
+        const int64_t row = nl * kTiles22PerImg + ty * kTiles22X + tx;
+        float t[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                t[r][j] = __ldg(M + (((int64_t)(2 * j + r) * (kGateCols / 128) + ct) * rows_pad + row) * 128 + threadIdx.x);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float *o = xg + ((n * kH + 2 * ty + r) * kW + 2 * tx) * (int64_t)kGateCols + ct * 128 + threadIdx.x;
+            o[0] = ((t[r][0] + t[r][1]) + t[r][2]) + b;
+            o[kGateCols] = ((t[r][1] - t[r][2]) - t[r][3]) + b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Head, part 1 (predict_head.forward :141-150): per pixel, the channel dot products of
 // feat with sal_layer_2, sal_layer_3 and with the <= 4 drt_layer_1 taps under which the
 // pixel falls (7x7 kernel, stride 5, pad 2 -> 6x8 windows).  One warp per (image, head, pixel).
@@ -1055,7 +1187,8 @@ static Workspace carve(void *base, int64_t N, int S, int HD, int steps) {
     w.sp_mem = (float *)take(N * S * kHW * 4);
     w.se_mem = (float *)take(N * S * kE * 4);
     w.drt_pre = (float *)take(N * HD * 48 * 4);
-    w.rows_pad = (N * kTilesPerImg + 127) / 128 * 128;
+    // Winograd tiles of a GEMM launch: N * 150 for the h-gates (F(2x4)), ceil(N / 2) * 300 for half a wave of x-gates (F(2x2))
+    w.rows_pad = ((N + 1) / 2 * kTiles22PerImg + 127) / 128 * 128;
     // the direct routes' gate pre-activations (acc, 9.8 MB per image) and the Winograd routes' operands and planes
     // (u, wm: 22 MB per image) are never live in the same decode: one region serves both
     const int64_t wino_start = o;
@@ -1198,8 +1331,11 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
     //    output transform): measured end to end, Winograd x-gates double the error of the probabilities;
     // 2: direct implicit GEMM for both;  3: Winograd for both (the round-1 product path, kept for comparison)
     // 4: Winograd for both, the x-gate GEMM with 8-k-step accumulators (wino_gemm_tc_kernel<4>)
-    const bool wino = io->use_tensor_cores == 1 || io->use_tensor_cores == 3 || io->use_tensor_cores == 4;
+    // 5: Winograd F(2x4) for the h-gates, direct implicit GEMM for the x-gates (the product path before F(2x2))
+    const bool wino = io->use_tensor_cores == 1 || io->use_tensor_cores == 3 || io->use_tensor_cores == 4 ||
+                      io->use_tensor_cores == 5;
     const bool wino_x = io->use_tensor_cores == 3 || io->use_tensor_cores == 4;
+    const bool wino_x22 = io->use_tensor_cores == 1;
     const bool wino_x_fine = io->use_tensor_cores == 4;
     const int64_t NP = N * kHW;
     if (wino) SPB_CUDA(cudaFuncSetAttribute(wino_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));
@@ -1219,6 +1355,20 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
                              kGateCols, w->inv_scale_wx, s, wino_x_fine));
         wino_output_kernel<<<dim3(kTilesY, (unsigned)N, kGateCols / 128), 128, 0, s>>>(ws.wm, ws.rows_pad, w->bias_gate, ws.xg);
         SPB_LAUNCH_CHECK();
+    } else if (wino_x22) {
+        // Winograd F(2x2,3x3), half a wave per pass (16 x 300 tiles per image fit the h-gate GEMMs' buffers then)
+        const int64_t half_n = (N + 1) / 2;
+        for (int64_t n0 = 0; n0 < N; n0 += half_n) {
+            const int64_t nl = N - n0 < half_n ? N - n0 : half_n;
+            const int64_t rp = (nl * kTiles22PerImg + 127) / 128 * 128;
+            wino_input22_kernel<<<(unsigned)(nl * kTilesY), 256, 0, s>>>(ws.vf_hi, ws.vf_lo, ws.u_hi, ws.u_lo, rp, n0);
+            SPB_LAUNCH_CHECK();
+            SPB_TRY(wino_gemm_tc(ws.u_hi, ws.u_lo, (const __half *)w->wwx2_hi, (const __half *)w->wwx2_lo, ws.wm, rp,
+                                 kGateCols, w->inv_scale_wx2, s, false, 4));
+            wino_output22_kernel<<<dim3(kTilesY, (unsigned)nl, kGateCols / 128), 128, 0, s>>>(ws.wm, rp, w->bias_gate,
+                                                                                          ws.xg, n0);
+            SPB_LAUNCH_CHECK();
+        }
     } else {
         ConvGemmArgs a{ws.vf_hi, ws.vf_lo, (const __half *)w->wx_hi, (const __half *)w->wx_lo, nullptr, kGateCols,
                        w->bias_gate, ws.xg, kGateCols, (int)N, kGateCols, 3, w->inv_scale_x};

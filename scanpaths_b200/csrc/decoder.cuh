@@ -55,7 +55,8 @@ int conv_gemm_simt(const ConvGemmArgs &a, cudaStream_t s);
 int conv_gemm_tc(const ConvGemmArgs &a, cudaStream_t s);     // tcgen05 / TMEM / TMA (conv_tc.cu)
 // the 24 Winograd F(2x4,3x3) per-position GEMMs + the row half of the output transform (conv_tc.cu):
 // u [24][rows_pad][512], w [24*cols][512] fp16 pairs (position 4j+i) -> out [12][cols/128][rows_pad][128] fp32
+// pos_j = 4: the 16 positions of F(2x2,3x3) (u [16][rows_pad][512], w [16*cols][512] -> out [8][...])
 int wino_gemm_tc(const __half *u_hi, const __half *u_lo, const __half *w_hi, const __half *w_lo, float *out,
-                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain = false);
+                 int64_t rows_pad, int cols, float inv_scale, cudaStream_t s, bool fine_drain = false, int pos_j = 6);
 
 }  // namespace spb

@@ -92,6 +92,12 @@ def prepare_weights(sd, task: str, device):
         return _interleave_gates(mats).view(2048, 24, 512).permute(1, 0, 2).reshape(24 * 2048, 512)
     t["ww_hi"], t["ww_lo"], isw = split_pair(wino_rows(GATES_H))
     t["wwx_hi"], t["wwx_lo"], iswx = split_pair(wino_rows(GATES_X))
+    # Winograd F(2x2,3x3) weights of the x-gates (the product path's loop-invariant convolution): G2 g G2^T,
+    # 16 positions 4j+i, [16 * 2048, 512]
+    mats22 = [torch.einsum("ia,ocab,jb->ojic", G2, f("lstm.%s.weight" % g).double(), G2).reshape(512, 16 * 512)
+              for g in GATES_X]
+    t["wwx2_hi"], t["wwx2_lo"], iswx2 = split_pair(
+        _interleave_gates(mats22).view(2048, 16, 512).permute(1, 0, 2).reshape(16 * 2048, 512))
     t["wx_hi"], t["wx_lo"], isx = split_pair(wx)
     t["wh_hi"], t["wh_lo"], ish = split_pair(wh)
     t["wp_hi"], t["wp_lo"], isp = split_pair(wp)
@@ -170,7 +176,7 @@ def prepare_weights(sd, task: str, device):
     bd2 = sd["object_head.drt_layer_2.bias"].detach().reshape(-1)
     w.bd2_mu, w.bd2_sigma = float(bd2[0]), float(bd2[1])
     w.inv_scale_x, w.inv_scale_h, w.inv_scale_p, w.inv_scale_w, w.inv_scale_wx, w.inv_scale_23 = isx, ish, isp, isw, iswx, is23
-    w.inv_scale_m, w.inv_scale_se = ism, isse
+    w.inv_scale_m, w.inv_scale_se, w.inv_scale_wx2 = ism, isse, iswx2
     w.n_streams = w.n_heads = len(streams)
     w.n_weight_sets = len(sets)
     return t, w

@@ -16,7 +16,7 @@ for scale in (1.0, 2.0, 4.0):
         p32 = OD.decode(sd, vf.float(), "OSIE", steps=T)["all_actions_prob"].double().numpy()
     rel = lambda a: float((np.abs(a - p64) / p64).max())
     line = ["scale %g  f32-ref %.2e" % (scale, rel(p32))]
-    for mode in (1, 2, 3, 4):  # 1 = product path (Winograd h, direct x), 2 = direct, 3 = Winograd both, 4 = Winograd both, fine-drain x
+    for mode in (1, 5, 2, 3, 4):  # 1 = product path (Winograd F(2x4) h, F(2x2) x), 5 = F(2x4) h + direct x, 2 = direct, 3 = F(2x4) both, 4 = same, fine-drain x
         try:
             p = CudaDecoder(sd, "OSIE", T, dev, wave=1, use_tensor_cores=mode).decode(vf.to(dev))[0][0]
             line.append("mode%d %.2e" % (mode, rel(p.double().cpu().numpy())))

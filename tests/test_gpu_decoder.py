@@ -134,13 +134,14 @@ def _decode_case(name, use_tc, golden_dir, steps=None):
 
 
 @pytest.mark.parametrize("name", ["coco", "air", "osie"])
-@pytest.mark.parametrize("use_tc", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("use_tc", [0, 1, 2, 3, 4, 5])
 def test_decode_matches_reference_fp64(lib, golden_dir, name, use_tc):
     """use_tc: 0 = SIMT fp32 check kernels with the explicit 5x5 layer (an independent route to the
-    same numbers), 1 = the product path (tcgen05: Winograd h-gate GEMMs, direct x-gate GEMM, composed head),
-    2 = direct 3x3 implicit GEMM for both, 3 = Winograd for both.  All T = 16 steps of every variant."""
+    same numbers), 1 = the product path (tcgen05: Winograd F(2x4) h-gate GEMMs, Winograd F(2x2) x-gate GEMM,
+    composed head), 2 = direct 3x3 implicit GEMM for both, 3 = Winograd F(2x4) for both (4: finer x-gate
+    accumulators), 5 = F(2x4) h-gates + direct x-gates.  All T = 16 steps of every variant."""
     worst = _decode_case(name, use_tc, golden_dir)
-    print(name, ["simt", "product", "tc-direct", "tc-winograd", "tc-winograd-fine-x"][use_tc], worst)
+    print(name, ["simt", "product", "tc-direct", "tc-winograd", "tc-winograd-fine-x", "tc-winograd-h-direct-x"][use_tc], worst)
     _record_margin("golden_%s_mode%d" % (name, use_tc), worst)
     for k, v in worst.items():
         if k.endswith("ref_f32_prob"):
@@ -206,7 +207,7 @@ def test_decode_other_seeds_and_feature_scales(lib, seed, scale):
         p64 = OD.decode(sd, vf.double(), "OSIE", steps=T)["all_actions_prob"].numpy()
         p32 = OD.decode(sd, vf.float(), "OSIE", steps=T)["all_actions_prob"].double().numpy()
     ref_err = float((np.abs(p32 - p64) / p64).max())
-    for mode in (2, 3, 1):                   # tcgen05 direct, Winograd for both, product path
+    for mode in (2, 3, 5, 1):                # tcgen05 direct, Winograd F(2x4) for both, F(2x4) h + direct x, product path
         dec = CudaDecoder(sd, "OSIE", T, dev, wave=1, use_tensor_cores=mode)
         probs, _, _, _ = dec.decode(vf.to(dev))
         err = float((np.abs(probs[0].double().cpu().numpy() - p64) / p64).max())
