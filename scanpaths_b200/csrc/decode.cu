@@ -512,12 +512,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 128-channel group), thread = channel, loop over the 10 tiles of the row; per tile and gate the 12 planes
 // t[r][j] = (A2^T m)[r][j] of the GEMM (coalesced 128-byte lines) give the 2 x 4 pre-activations t . A4.
 // HAS_M = false means h = 0 (first step).  HBM: 12 x 2 KB (M) + 8 x 8 KB (xg) + c, h per tile and 128 channels.
+// Two streams (AiR): the 54 rank-1 weights of a thread live in shared memory ([stream][gate][tap][channel], each
+// thread reads back only what it wrote) instead of registers -- 168 -> ~115 registers, 4 blocks per SM instead of 3.
 template <int S, bool HAS_M>
-__global__ void __launch_bounds__(128, S == 1 ? 4 : 3)
+__global__ void __launch_bounds__(128, 4)
 lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float *__restrict__ xg,
                       const float *__restrict__ V, const float *__restrict__ sp_mem, float *__restrict__ c,
                       __half *__restrict__ h_hi, __half *__restrict__ h_lo) {
     __shared__ float halo[S][4][42];
+    __shared__ float vs[S == 1 ? 1 : S * 27][S == 1 ? 1 : 128];
     const int64_t n = blockIdx.y;
     const int ty = blockIdx.x;
     const int ch = blockIdx.z * 128 + threadIdx.x;
@@ -526,14 +529,17 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
         const int yy = 2 * ty - 1 + hy, xx = hx - 1;
         halo[st][hy][hx] = (yy >= 0 && yy < kH && xx >= 0 && xx < kW) ? sp_mem[(n * S + st) * kHW + yy * kW + xx] : 0.0f;
     }
-    float v[S][3][9];
+    float v[1][3][9];                                // S == 1: in registers (S == 2: unused)
 #pragma unroll
     for (int st = 0; st < S; ++st)
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9)
-                v[st][g][t9] = V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9];
+            for (int t9 = 0; t9 < 9; ++t9) {
+                const float x = V[(((n * S + st) * 3 + g) * (int64_t)kE + ch) * 9 + t9];
+                if (S == 1) v[0][g][t9] = x;
+                else vs[(st * 3 + g) * 9 + t9][threadIdx.x] = x;
+            }
     __syncthreads();
     const int gc = gate_col(ch, 0);
     for (int tx = 0; tx < kTilesX; ++tx) {
@@ -583,9 +589,15 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9) {
                         const float sv = halo[st][r + t9 / 3][4 * tx + ox + t9 % 3];
-                        r0 = fmaf(v[st][0][t9], sv, r0);
-                        r1 = fmaf(v[st][1][t9], sv, r1);
-                        r2 = fmaf(v[st][2][t9], sv, r2);
+                        if (S == 1) {
+                            r0 = fmaf(v[0][0][t9], sv, r0);
+                            r1 = fmaf(v[0][1][t9], sv, r1);
+                            r2 = fmaf(v[0][2][t9], sv, r2);
+                        } else {
+                            r0 = fmaf(vs[(st * 3 + 0) * 9 + t9][threadIdx.x], sv, r0);
+                            r1 = fmaf(vs[(st * 3 + 1) * 9 + t9][threadIdx.x], sv, r1);
+                            r2 = fmaf(vs[(st * 3 + 2) * 9 + t9][threadIdx.x], sv, r2);
+                        }
                     }
                     p0 += r0; p1 += r1; p2 += r2;
                 }
