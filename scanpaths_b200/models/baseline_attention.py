@@ -271,8 +271,9 @@ class CudaDecoder:
         self.lib = _lib.load()
         self.task, self.steps, self.wave = task, int(steps), int(wave)
         self.device = torch.device(device)
-        # 0 = SIMT check path (explicit 5x5 layer); 1 = product path: tcgen05, Winograd h-gates + direct x-gates +
-        # composed head; 2 = tcgen05 direct 3x3 for both; 3 = Winograd for both (see csrc/decode.cu)
+        # 0 = SIMT check path (explicit 5x5 layer); 1 = product path: tcgen05, Winograd F(2x4) h-gates + Winograd
+        # F(2x2) x-gates + composed head; 2 = tcgen05 direct 3x3 for both; 3 / 4 = F(2x4) for both; 5 = F(2x4)
+        # h-gates + direct x-gates (see csrc/decode.cu)
         self.use_tensor_cores = int(use_tensor_cores)
         if self.use_tensor_cores:
             self.acc_trunc_fix = calibrate_acc_trunc_fix(self.device)
