@@ -293,8 +293,7 @@ lstm_cell_kernel(const float *__restrict__ acc, const float *__restrict__ xg, co
 // 120 pixels, the tile's spatial-memory halo sits in shared memory, and every global access is a
 // fully coalesced 128-byte line per warp (acc / xg: 4 gate segments of 32 channels, gate_col order).
 // Algorithmic HBM traffic: 26.8 MB per image-step (acc 9.8 + xg 9.8 + c 2.4 r + 2.4 w + h 2.4).
-// Blocks are 128 threads (one 128-channel group): small enough (8 K registers, < 1 KB smem) to be
-// co-resident with a persistent GEMM CTA of the other half-wave's stream (see pipeline.py).
+// Blocks are 128 threads (one 128-channel group).
 template <int S>
 __global__ void __launch_bounds__(128, S == 1 ? 8 : 4)
 lstm_cell_tiled_kernel(const float *__restrict__ acc, const float *__restrict__ xg, const float *__restrict__ V,

@@ -443,9 +443,10 @@ int score_pairs_g8(const spb_path_pack &A, const spb_path_pack &B, const int32_t
     if (cfg.sm.GapValue != 0.0 || B.lmax > kG * 4) return SPB_OK;
     const PairLayout L = make_layout(A.lmax, B.lmax);
     const int ntab_bytes = (cfg.sm.Xbin * cfg.sm.Ybin * 8 + 15) & ~15;
-    // warps per block: 4 by default.  One-warp blocks (21 KB of shared memory, 5 K registers) are small enough to sit
-    // next to a persistent GEMM CTA (193 KB, 54 K registers) on the same SM: with SPB_SCORE_WARPS=1 the pipeline's
-    // tail stream scores wave w in the issue slots the tensor-bound gate GEMMs of wave w+1 leave idle.
+    // warps per block: 4 by default; SPB_SCORE_WARPS=1|2|4 picks the launch size.  (One-warp blocks -- 21 KB of shared
+    // memory, 5 K registers -- were meant to run beside a resident gate-GEMM CTA of the next wave; they cannot: the
+    // register file is partitioned per SM sub-partition and the GEMM's 10 warps x 168 registers fill two of the
+    // four.  Measured: no gain)
     static int wpb_env = -1;
     if (wpb_env < 0) {
         const char *e = getenv("SPB_SCORE_WARPS");
