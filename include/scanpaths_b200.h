@@ -126,6 +126,14 @@ typedef struct spb_path_pack {
  *   symbols; spb_score_workspace_bytes(max human nwd) bytes, may be NULL otherwise.
  *   d_err: device int32 set non-zero if a pair needed more workspace than given.   */
 int64_t spb_score_workspace_bytes(int64_t max_human_nwd);
+
+/* The F matrix of ScanMatch.match for ONE pair of symbol strings (scanmatch.py:138-150), what the single-pair
+ * API needs for the alignment it returns (scanmatch.py:152-195; the O(n + m) traceback itself runs on the host):
+ *   d_F [(n+1), (m+1)] f64 row-major, F[i][0] = GapValue * (i + 1), F[0][j] = GapValue * (j + 1),
+ *   F[i][j] = max(F[i-1][j-1] + Sub[a[i-1]][b[j-1]], F[i][j-1] + GapValue, F[i-1][j] + GapValue); bit-identical
+ *   to the reference's numpy loop.  Symbols must lie in [0, Xbin * Ybin). */
+int spb_scanmatch_matrix(const int32_t *d_a, int32_t n, const int32_t *d_b, int32_t m, const spb_score_cfg *cfg,
+                         double *d_F, spb_stream stream);
 int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const int32_t *d_pair_h,
                     const int32_t *d_pair_s, int64_t n_pairs, const spb_score_cfg *cfg, double *d_scores,
                     void *d_workspace, int64_t workspace_bytes, int32_t *d_err, spb_stream stream);

@@ -25,7 +25,8 @@ import numpy as np
 # ScanMatch
 # --------------------------------------------------------------------------
 class ScanMatchOracle:
-    """Restates ``ScanMatch`` (scanmatch.py:39-197); score only, no traceback."""
+    """Restates ``ScanMatch`` (scanmatch.py:39-197): ``match_score`` is what the drivers use, ``match`` also
+    returns the alignment and the (transposed) F matrix like the reference's."""
 
     _KEYS = ("Xres", "Yres", "Xbin", "Ybin", "Threshold", "GapValue", "TempBin", "Offset")
 
@@ -79,10 +80,8 @@ class ScanMatchOracle:
             seq = np.array(out)
         return seq
 
-    def match_score(self, A, B):
-        # scanmatch.py:135-150, 190-193 (the callers drop align and F).
-        A = np.asarray(A).astype(np.int64)
-        B = np.asarray(B).astype(np.int64)
+    def _fill(self, A, B):
+        # scanmatch.py:135-150: borders gap * (index + 1), then the three-way maximum
         n, m = len(A), len(B)
         gap = self.GapValue
         F = np.zeros((n + 1, m + 1))
@@ -97,11 +96,43 @@ class ScanMatchOracle:
                 up = F[i - 1, j] + gap
                 left = F[i, j - 1] + gap
                 F[i, j] = max(diag, left, up)
+        return F
+
+    def match_score(self, A, B):
+        # scanmatch.py:135-150, 190-193 (the callers drop align and F).
+        A = np.asarray(A).astype(np.int64)
+        B = np.asarray(B).astype(np.int64)
+        F = self._fill(A, B)
         with np.errstate(invalid="ignore", divide="ignore"):
-            return np.float64(np.max(F)) / np.float64(np.max(sub) * max(m, n))
+            return np.float64(np.max(F)) / np.float64(np.max(self.SubMatrix) * max(len(B), len(A)))
+
+    @staticmethod
+    def traceback(F, A, B, sub, gap):
+        """scanmatch.py:152-185, 195: walk back from F[n, m] -- a diagonal step when the cell equals the diagonal
+        neighbour plus the substitution score, else a step in A when it equals F[i-1, j] + gap, else a step in
+        B; the rest of either string is appended; -1 marks a gap.  Returns [steps, 2] in forward order."""
+        i, j = len(A), len(B)
+        ra, rb = [], []
+        while i > 0 and j > 0:
+            if F[i, j] == F[i - 1, j - 1] + sub[A[i - 1], B[j - 1]]:
+                ra.append(A[i - 1]); rb.append(B[j - 1]); i -= 1; j -= 1
+            elif F[i, j] == F[i - 1, j] + gap:
+                ra.append(A[i - 1]); rb.append(-1); i -= 1
+            else:
+                ra.append(-1); rb.append(B[j - 1]); j -= 1
+        while i > 0:
+            ra.append(A[i - 1]); rb.append(-1); i -= 1
+        while j > 0:
+            ra.append(-1); rb.append(B[j - 1]); j -= 1
+        return np.array([ra[::-1], rb[::-1]], dtype=np.float64).T.reshape(-1, 2)
 
     def match(self, A, B):
-        return self.match_score(A, B), None, None
+        A = np.asarray(A).astype(np.int64)
+        B = np.asarray(B).astype(np.int64)
+        F = self._fill(A, B)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            score = np.float64(np.max(F)) / np.float64(np.max(self.SubMatrix) * max(len(B), len(A)))
+        return score, self.traceback(F, A, B, self.SubMatrix, self.GapValue), F.transpose()
 
 
 # --------------------------------------------------------------------------

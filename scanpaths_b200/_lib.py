@@ -60,6 +60,7 @@ SYMBOLS = {
     "spb_scanmatch_tables": (C.c_int, [C.POINTER(ScanMatchCfg), P, P, P, P, P]),
     "spb_prep_paths": (C.c_int, [P, P, I64, I32, C.POINTER(ScoreCfg), P, P, P, P, P, P]),
     "spb_score_workspace_bytes": (I64, [I64]),
+    "spb_scanmatch_matrix": (C.c_int, [P, I32, P, I32, C.POINTER(ScoreCfg), P, P]),
     "spb_score_pairs": (C.c_int, [C.POINTER(PathPack), C.POINTER(PathPack), P, P, I64, C.POINTER(ScoreCfg), P, P,
                                   I64, P, P]),
     "spb_reduce_pairs_eval": (C.c_int, [P, P, I64, I32, P, P, P]),

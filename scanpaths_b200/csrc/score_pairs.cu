@@ -500,6 +500,48 @@ extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *
     return SPB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// ScanMatch.match's F matrix of ONE pair (scanmatch.py:138-150), for the single-pair API's alignment
+// (utils/evaltools/scanmatch.py::ScanMatch.match): F [(n+1), (m+1)] row-major, borders GapValue * (index + 1),
+// F[i][j] = max(F[i-1][j-1] + Sub[a[i-1]][b[j-1]], F[i][j-1] + gap, F[i-1][j] + gap) in f64, the reference's
+// operations -- bit-identical.  One block sweeps the anti-diagonals (every cell of a diagonal depends on the two
+// before it only); the O(n + m) traceback runs on the host from this matrix.
+// ---------------------------------------------------------------------------
+namespace spb {
+__global__ void __launch_bounds__(256)
+scanmatch_matrix_kernel(const int32_t *__restrict__ a, int n, const int32_t *__restrict__ b, int m,
+                        const double *__restrict__ sub_delta, int xbin, double gap, double *F) {
+    const int ld = m + 1;
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) F[(int64_t)i * ld] = gap * (double)(i + 1);
+    for (int j = threadIdx.x; j <= m; j += blockDim.x) F[j] = gap * (double)(j + 1);
+    __syncthreads();
+    for (int d = 2; d <= n + m; ++d) {
+        const int i_lo = max(1, d - m), i_hi = min(n, d - 1);
+        for (int i = i_lo + threadIdx.x; i <= i_hi; i += blockDim.x) {
+            const int j = d - i;
+            const int sa = a[i - 1], sb = b[j - 1];
+            const double s = sub_delta[abs(sa / xbin - sb / xbin) * xbin + abs(sa % xbin - sb % xbin)];
+            const double mt = F[(int64_t)(i - 1) * ld + j - 1] + s;
+            const double ins = F[(int64_t)i * ld + j - 1] + gap;
+            const double del = F[(int64_t)(i - 1) * ld + j] + gap;
+            F[(int64_t)i * ld + j] = fmax(fmax(mt, ins), del);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace spb
+
+extern "C" int spb_scanmatch_matrix(const int32_t *d_a, int32_t n, const int32_t *d_b, int32_t m,
+                                    const spb_score_cfg *cfg, double *d_F, spb_stream stream) {
+    SPB_CHECK_ARG(cfg != nullptr && cfg->d_sub_delta != nullptr, "cfg tables missing");
+    SPB_CHECK_ARG(n >= 0 && m >= 0 && d_F != nullptr, "bad sizes");
+    SPB_CHECK_ARG((n == 0 || d_a) && (m == 0 || d_b), "null device pointer");
+    spb::scanmatch_matrix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_a, n, d_b, m, cfg->d_sub_delta, cfg->sm.Xbin,
+                                                                      cfg->sm.GapValue, d_F);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
 static int reduce_blocks(int64_t n_groups) {
     int64_t blocks = (n_groups + 255) / 256;
     const int64_t cap = (int64_t)spb::num_sms() * 4;

@@ -167,6 +167,26 @@ def pack_paths(paths, cfg: ScoreConfig, lmax=None) -> PathPack:
     return prep_paths(torch.from_numpy(arr).to(cfg.device), torch.from_numpy(lens).to(cfg.device), cfg)
 
 
+def scanmatch_matrix(A, B, cfg: "ScoreConfig"):
+    """ScanMatch.match's F matrix of one pair of symbol strings (scanmatch.py:138-150) from the device kernel
+    spb_scanmatch_matrix: numpy [(n+1), (m+1)] f64, bit-identical to the reference's."""
+    A = np.asarray(A).astype(np.int64).reshape(-1)
+    B = np.asarray(B).astype(np.int64).reshape(-1)
+    nb = int(cfg.cfg.sm.Xbin) * int(cfg.cfg.sm.Ybin)
+    if (len(A) and (A.min() < 0 or A.max() >= nb)) or (len(B) and (B.min() < 0 or B.max() >= nb)):
+        raise IndexError("symbol outside the %d bins of the substitution matrix" % nb)      # the reference's SubMatrix[A, B]
+    dev = cfg.device
+    n, m = len(A), len(B)
+    da = torch.from_numpy(A.astype(np.int32)).to(dev)
+    db = torch.from_numpy(B.astype(np.int32)).to(dev)
+    F = torch.empty((n + 1, m + 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().spb_scanmatch_matrix(_lib.ptr(da) if n else None, n, _lib.ptr(db) if m else None, m,
+                                                    C.byref(cfg.cfg), _lib.ptr(F), _lib.current_stream()),
+                   "spb_scanmatch_matrix")
+    return F.cpu().numpy()
+
+
 class Workspace:
     """Boundary-column workspace for with-duration strings longer than 256 symbols."""
 

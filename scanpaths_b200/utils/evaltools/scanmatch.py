@@ -2,16 +2,16 @@
 
 Same constructor keywords, attributes and methods as the reference's
 ``ScanMatch`` (scanmatch.py:39-197); the work runs in csrc/prep.cu and
-csrc/score_pairs.cu.  ``match`` returns ``(score, None, None)``: every caller in
-the reference discards the alignment and the F matrix
-(OSIE/utils/evaluation.py:186,192), so only the score is computed.
-For throughput use ``scanpaths_b200.scoring`` / ``utils.evaluation`` (batched);
-this class scores one pair per call.
+csrc/score_pairs.cu.  ``match`` returns ``(score, align, F)`` like the
+reference's: the F matrix comes from the device (spb_scanmatch_matrix, bit-identical),
+the O(n + m) walk back through it runs on the host.  Every caller in the reference
+discards align and F (OSIE/utils/evaluation.py:186,192): for throughput use
+``scanpaths_b200.scoring`` / ``utils.evaluation`` (batched, score only); this class
+handles one pair per call.
 """
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 from ... import scoring as S
 
@@ -63,17 +63,29 @@ class ScanMatch(object):
             return np.repeat(sym, pack.run[0, :L].cpu().numpy())
         return sym
 
-    # -- scanmatch.py:135-197 (score only)
+    # -- scanmatch.py:135-197
     def match(self, A, B):
         A = np.asarray(A).astype(np.int64).reshape(-1)
         B = np.asarray(B).astype(np.int64).reshape(-1)
-        packs = [_rle_pack(A, self._config()), _rle_pack(B, self._config())]
-        if packs[1].lmax > 256 and packs[0].lmax <= 256:                 # NW is symmetric in (A, B)
-            packs = packs[::-1]
-        dev = self._config().device
-        z = torch.zeros(1, dtype=torch.int32, device=dev)
-        out = S.score_pairs(packs[0], packs[1], z, z, self._config())
-        return float(out[0, 0].item()), None, None
+        n, m = len(A), len(B)
+        F = S.scanmatch_matrix(A, B, self._config())                     # [(n+1), (m+1)], scanmatch.py:138-150
+        # walk back from F[n, m] (:152-185): diagonal when the cell is its diagonal neighbour plus the
+        # substitution score, else along A when it is F[i-1, j] + GapValue, else along B; -1 marks a gap
+        sub, gap = self.SubMatrix, self.GapValue
+        i, j, ra, rb = n, m, [], []
+        while i > 0 and j > 0:
+            if F[i, j] == F[i - 1, j - 1] + sub[A[i - 1], B[j - 1]]:
+                ra.append(A[i - 1]); rb.append(B[j - 1]); i -= 1; j -= 1
+            elif F[i, j] == F[i - 1, j] + gap:
+                ra.append(A[i - 1]); rb.append(-1); i -= 1
+            else:
+                ra.append(-1); rb.append(B[j - 1]); j -= 1
+        ra += list(A[:i][::-1]) + [-1] * j
+        rb += [-1] * i + list(B[:j][::-1])
+        align = np.array([ra[::-1], rb[::-1]], dtype=np.float64).T.reshape(-1, 2)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            score = np.float64(np.max(F)) / np.float64(np.max(sub) * max(m, n))        # :190-193
+        return score, align, F.transpose()
 
     def maskFromArray(self, array):
         """scanmatch.py:199-200: `array` [Yres, Xres] replaces the grid mask; fixationToSequence then reads the
@@ -84,25 +96,3 @@ class ScanMatch(object):
 
     def subMatrixFromArray(self, array):
         self.SubMarix = array                                            # reference typo kept: it has no effect there either
-
-
-def _rle_pack(seq, cfg):
-    """Explicit symbol string -> PathPack in run-length form (sym, run)."""
-    dev = cfg.device
-    if len(seq) == 0:
-        sym, run = np.zeros(1, np.uint8), np.zeros(1, np.int32)
-        n = 0
-    else:
-        cut = np.flatnonzero(np.diff(seq)) + 1
-        starts = np.concatenate([[0], cut])
-        sym = seq[starts].astype(np.uint8)
-        run = np.diff(np.concatenate([starts, [len(seq)]])).astype(np.int32)
-        n = len(sym)
-    L = len(sym)
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
-    return S.PathPack(xyd=torch.zeros((1, L, 3), dtype=torch.float64, device=dev),
-                      len=torch.tensor([n], dtype=torch.int32, device=dev),
-                      sym=t(sym[None], torch.uint8), run=t(run[None], torch.int32),
-                      nwd=torch.tensor([int(len(seq))], dtype=torch.int32, device=dev),
-                      sed=torch.zeros((1, L), dtype=torch.int32, device=dev),
-                      xyn=torch.zeros((1, L, 2), dtype=torch.float64, device=dev))

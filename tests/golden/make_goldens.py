@@ -318,8 +318,44 @@ def gen_air_eval():
     print("air eval goldens written")
 
 
+def gen_align():
+    """ScanMatch.match's full return value (score, alignment, transposed F matrix; scanmatch.py:135-197) for the
+    .mat fixture in the evaluation configuration (with- and without-duration strings), a GapValue != 0 case and
+    short strings -- every reference caller drops align and F, the mirror returns them all the same."""
+    import scipy.io as sio
+    ns = refload.load_reference("OSIE")
+    SM = ns.scanmatch.ScanMatch
+    mat = sio.loadmat(os.path.join(ns.tree, "utils/evaltools/ScanMatch_DataExample.mat"))
+    data = [np.asarray(mat["data%d" % i], dtype=np.float64) * [0.3125, 0.3125, 1.0] for i in (1, 2, 3)]
+    cfg = dict(Xres=320, Yres=240, Xbin=16, Ybin=12, Offset=(0, 0), Threshold=3.5)
+    cases = []
+    for gap, tb in ((0.0, 50), (0.0, 0), (-0.5, 0), (-1.25, 50), (0.75, 0)):
+        kw = dict(cfg, GapValue=gap)
+        if tb:
+            kw["TempBin"] = tb
+        obj = SM(**kw)
+        for i, j in ((0, 1), (1, 2), (2, 2)):
+            cases.append((obj, gap, tb, obj.fixationToSequence(data[i]).astype(np.int32),
+                          obj.fixationToSequence(data[j]).astype(np.int32)))
+    obj = SM(**cfg)
+    rng = np.random.default_rng(5)
+    cases.append((obj, 0.0, 0, np.array([17], np.int32), np.array([17, 3, 190], np.int32)))
+    cases.append((obj, 0.0, 0, rng.integers(0, 192, 7).astype(np.int32), np.array([5], np.int32)))
+    cases.append((obj, 0.0, 0, rng.integers(0, 192, 40).astype(np.int32), rng.integers(0, 192, 33).astype(np.int32)))
+    out = {"n_cases": np.int64(len(cases))}
+    for k, (o, gap, tb, A, B) in enumerate(cases):
+        score, align, F = o.match(A, B)
+        out["c%d_A" % k], out["c%d_B" % k] = A, B
+        out["c%d_gap" % k], out["c%d_tempbin" % k] = np.float64(gap), np.int64(tb)
+        out["c%d_score" % k], out["c%d_align" % k], out["c%d_F" % k] = np.float64(score), np.asarray(align), np.asarray(F)
+    np.savez_compressed(os.path.join(HERE, "scoring_align.npz"), **out)
+    print("alignment goldens:", len(cases), "cases; F shapes", [out["c%d_F" % k].shape for k in range(len(cases))][:6])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("align", "all"):
+        gen_align()
     if what in ("scoring", "all"):
         gen_scoring()
     if what in ("eval", "all"):

@@ -221,6 +221,25 @@ def test_mirror_single_pair_api(S, golden_dir):
         ScanMatch(Foo=1)
 
 
+def test_mirror_match_returns_alignment_and_matrix(S, golden_dir):
+    """ScanMatch.match -> (score, align, F) as the reference returns them (scanmatch.py:135-197): the F matrix from
+    spb_scanmatch_matrix, the walk back on the host.  All three exact against the recorded reference outputs:
+    with / without duration strings of the .mat fixture, GapValue -0.5 / -1.25 / +0.75, short strings."""
+    from scanpaths_b200.utils.evaltools.scanmatch import ScanMatch
+    g = np.load(os.path.join(golden_dir, "scoring_align.npz"))
+    for k in range(int(g["n_cases"])):
+        sm = ScanMatch(Xres=320, Yres=240, Xbin=16, Ybin=12, Offset=(0, 0), Threshold=3.5, GapValue=float(g["c%d_gap" % k]))
+        score, align, F = sm.match(g["c%d_A" % k], g["c%d_B" % k])
+        assert score == g["c%d_score" % k], k
+        assert align.shape == g["c%d_align" % k].shape and np.array_equal(align, g["c%d_align" % k]), k
+        assert F.shape == g["c%d_F" % k].shape and np.array_equal(F, g["c%d_F" % k]), k
+    sm = ScanMatch(Xres=320, Yres=240, Xbin=16, Ybin=12)
+    with pytest.raises(IndexError):                       # the reference indexes SubMatrix[A, B]
+        sm.match(np.array([5, 400]), np.array([1]))
+    score, align, F = sm.match(np.array([], dtype=np.int64), np.array([3, 4]))      # one empty string
+    assert score == 0.0 and F.shape == (3, 1) and np.array_equal(align, [[-1, 3], [-1, 4]])
+
+
 def test_mirror_evaluation_drivers(S, golden_dir):
     from test_oracle_golden import _flat, _struct_lists
     from scanpaths_b200.utils import evaluation as E

@@ -85,6 +85,21 @@ def _flat(m):
                      m["VAME"]["STDE"], m["VAME"]["SED_best"], m["VAME"]["STDE_best"]])
 
 
+ALIGN_CFG = dict(Xres=320, Yres=240, Xbin=16, Ybin=12, Threshold=3.5)
+
+
+def test_match_alignment_and_matrix(golden_dir):
+    """ScanMatch.match's whole return value (score, alignment, transposed F; scanmatch.py:135-197) for the 18
+    recorded cases: with / without duration strings of the .mat fixture, three non-zero gap values, short strings."""
+    g = np.load(os.path.join(golden_dir, "scoring_align.npz"))
+    for k in range(int(g["n_cases"])):
+        o = O.ScanMatchOracle(GapValue=float(g["c%d_gap" % k]), **ALIGN_CFG)
+        score, align, F = o.match(g["c%d_A" % k], g["c%d_B" % k])
+        assert score == g["c%d_score" % k], k
+        assert np.array_equal(align, g["c%d_align" % k]), k
+        assert np.array_equal(F, g["c%d_F" % k]), k
+
+
 def test_eval_drivers(golden_dir):
     g = _load(golden_dir, "eval_drivers.npz")
     humans, preds, N, K, S = _struct_lists(g)
