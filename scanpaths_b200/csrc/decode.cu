@@ -561,7 +561,7 @@ lstm_cell_wino_kernel(const float *__restrict__ M, int64_t rows_pad, const float
             for (int ox = 0; ox < 4; ++ox) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xv[ox][g] = __ldg(xg + (pix0 + ox) * kGateCols + gc + g * 32);
-                cv[ox] = c[(pix0 + ox) * kE + ch];
+                cv[ox] = HAS_M ? c[(pix0 + ox) * kE + ch] : 0.0f;       // first step: c(0) = 0, never read
             }
             float pre[4][4];                          // [gate][ox] of output row r
 #pragma unroll
@@ -1386,9 +1386,9 @@ extern "C" int spb_decode(const spb_decoder_weights *w, const spb_decoder_io *io
         SPB_TRY(conv_gemm(a, tc, s));
     }
     prof_end(s);
-    SPB_CUDA(cudaMemsetAsync(ws.h_hi[0], 0, NP * kE * 2, s));
-    SPB_CUDA(cudaMemsetAsync(ws.h_lo[0], 0, NP * kE * 2, s));
-    SPB_CUDA(cudaMemsetAsync(ws.c, 0, NP * kE * 4, s));
+    // zero state: h(0) is never read (its convolution is skipped / exactly 0 and the first cell writes the other
+    // buffer); c(0) is read as 0 by the Winograd-route cell kernel itself, by the other cell kernels from memory
+    if (!wino) SPB_CUDA(cudaMemsetAsync(ws.c, 0, NP * kE * 4, s));
 
     auto feedback_tail = [&](int list_index) -> int {
         // spatial_embed / semantic_embed (:197-198, :336, :339) then the two memory attentions
