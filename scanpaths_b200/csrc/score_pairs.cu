@@ -510,7 +510,7 @@ extern "C" int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *
 namespace spb {
 __global__ void __launch_bounds__(256)
 scanmatch_matrix_kernel(const int32_t *__restrict__ a, int n, const int32_t *__restrict__ b, int m,
-                        const double *__restrict__ sub_delta, int xbin, double gap, double *F) {
+                        const double *__restrict__ sub_delta, int xbin, int nbins, double gap, double *F) {
     const int ld = m + 1;
     for (int i = threadIdx.x; i <= n; i += blockDim.x) F[(int64_t)i * ld] = gap * (double)(i + 1);
     for (int j = threadIdx.x; j <= m; j += blockDim.x) F[j] = gap * (double)(j + 1);
@@ -520,7 +520,9 @@ scanmatch_matrix_kernel(const int32_t *__restrict__ a, int n, const int32_t *__r
         for (int i = i_lo + threadIdx.x; i <= i_hi; i += blockDim.x) {
             const int j = d - i;
             const int sa = a[i - 1], sb = b[j - 1];
-            const double s = sub_delta[abs(sa / xbin - sb / xbin) * xbin + abs(sa % xbin - sb % xbin)];
+            // a symbol outside the bins (the reference raises IndexError; the Python mirror checks first) poisons its cells
+            const bool ok = (unsigned)sa < (unsigned)nbins && (unsigned)sb < (unsigned)nbins;
+            const double s = ok ? sub_delta[abs(sa / xbin - sb / xbin) * xbin + abs(sa % xbin - sb % xbin)] : nan("");
             const double mt = F[(int64_t)(i - 1) * ld + j - 1] + s;
             const double ins = F[(int64_t)i * ld + j - 1] + gap;
             const double del = F[(int64_t)(i - 1) * ld + j] + gap;
@@ -537,7 +539,7 @@ extern "C" int spb_scanmatch_matrix(const int32_t *d_a, int32_t n, const int32_t
     SPB_CHECK_ARG(n >= 0 && m >= 0 && d_F != nullptr, "bad sizes");
     SPB_CHECK_ARG((n == 0 || d_a) && (m == 0 || d_b), "null device pointer");
     spb::scanmatch_matrix_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_a, n, d_b, m, cfg->d_sub_delta, cfg->sm.Xbin,
-                                                                      cfg->sm.GapValue, d_F);
+                                                                      cfg->sm.Xbin * cfg->sm.Ybin, cfg->sm.GapValue, d_F);
     SPB_LAUNCH_CHECK();
     return SPB_OK;
 }
