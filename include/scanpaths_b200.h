@@ -134,6 +134,16 @@ int64_t spb_score_workspace_bytes(int64_t max_human_nwd);
  *   to the reference's numpy loop.  Symbols must lie in [0, Xbin * Ybin). */
 int spb_scanmatch_matrix(const int32_t *d_a, int32_t n, const int32_t *d_b, int32_t m, const spb_score_cfg *cfg,
                          double *d_F, spb_stream stream);
+
+/* The time-delay-embedding distances of ONE pair for every window length k = 1 .. min(Lh, Ls)
+ * (time_delay_embedding_distance, visual_attention_metrics.py:332-390; its callers euclidean_distance :205-218
+ * and scaled_time_delay_embedding_distance :444-492 are host arithmetic on this table):
+ *   d_h_xy [Lh, 2], d_s_xy [Ls, 2] f64 (x, y), no rescaling here;
+ *   d_out [min(Lh, Ls), 3] f64: (distance_mode 'Mean', distance_mode 'Hausdorff', sum of the first k point distances);
+ *   d_work: spb_tde_work_bytes(Lh, Ls) bytes. */
+int64_t spb_tde_work_bytes(int32_t Lh, int32_t Ls);
+int spb_tde_distances(const double *d_h_xy, int32_t Lh, const double *d_s_xy, int32_t Ls, double *d_work,
+                      int64_t work_bytes, double *d_out, spb_stream stream);
 int spb_score_pairs(const spb_path_pack *human, const spb_path_pack *sim, const int32_t *d_pair_h,
                     const int32_t *d_pair_s, int64_t n_pairs, const spb_score_cfg *cfg, double *d_scores,
                     void *d_workspace, int64_t workspace_bytes, int32_t *d_err, spb_stream stream);

@@ -182,8 +182,17 @@ def _window_distance(hs, ss):
     return dist.sum()
 
 
-def time_delay_embedding_distance(human, simulated, k):
-    """visual_attention_metrics.py:332-390, distance_mode='Mean'."""
+def euclidean_distance(human_scanpath, simulated_scanpath):
+    """visual_attention_metrics.py:205-218: sum of the point distances of two equally long scanpaths, else False."""
+    if len(human_scanpath) != len(simulated_scanpath):
+        return False
+    return _window_distance(human_scanpath, simulated_scanpath)
+
+
+def time_delay_embedding_distance(human, simulated, k=3, distance_mode="Mean"):
+    """visual_attention_metrics.py:332-390: every k-window of `simulated` looks for its nearest k-window of
+    `human` (distance / k); 'Mean' or 'Hausdorff' (max) over the simulated windows; False when k is longer than
+    a scanpath or the mode is unknown."""
     if len(human) < k or len(simulated) < k:
         return False
     per_window = []
@@ -194,7 +203,22 @@ def time_delay_embedding_distance(human, simulated, k):
             d = abs(_window_distance(simulated[i:i + k], human[j:j + k]))
             best = d if best is None or d < best else best
         per_window.append(best / k)
-    return sum(per_window) / len(per_window)
+    if distance_mode == "Mean":
+        return sum(per_window) / len(per_window)
+    if distance_mode == "Hausdorff":
+        return max(per_window)
+    return False
+
+
+def scaled_time_delay_embedding_distance(human_scanpath, simulated_scanpath, image):
+    """visual_attention_metrics.py:444-492: mean over k of the 'Mean' distances of the rescaled scanpaths."""
+    H = np.array(human_scanpath, dtype=np.float64, copy=True)
+    S = np.array(simulated_scanpath, dtype=np.float64, copy=True)
+    max_dim = float(max(np.shape(image)))
+    H[:, :2] /= max_dim
+    S[:, :2] /= max_dim
+    d = [time_delay_embedding_distance(H, S, k) for k in range(1, min(len(H), len(S)) + 1)]
+    return sum(d) / len(d) if d else None
 
 
 def scaled_time_delay_embedding_similarity(human_scanpath, simulated_scanpath, image):

@@ -61,6 +61,8 @@ SYMBOLS = {
     "spb_prep_paths": (C.c_int, [P, P, I64, I32, C.POINTER(ScoreCfg), P, P, P, P, P, P]),
     "spb_score_workspace_bytes": (I64, [I64]),
     "spb_scanmatch_matrix": (C.c_int, [P, I32, P, I32, C.POINTER(ScoreCfg), P, P]),
+    "spb_tde_work_bytes": (I64, [I32, I32]),
+    "spb_tde_distances": (C.c_int, [P, I32, P, I32, P, I64, P, P]),
     "spb_score_pairs": (C.c_int, [C.POINTER(PathPack), C.POINTER(PathPack), P, P, I64, C.POINTER(ScoreCfg), P, P,
                                   I64, P, P]),
     "spb_reduce_pairs_eval": (C.c_int, [P, P, I64, I32, P, P, P]),

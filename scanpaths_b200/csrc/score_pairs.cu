@@ -544,6 +544,72 @@ extern "C" int spb_scanmatch_matrix(const int32_t *d_a, int32_t n, const int32_t
     return SPB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The time-delay-embedding distances of ONE pair for every window length k (visual_attention_metrics.py:332-390),
+// for the single-pair API (time_delay_embedding_distance, scaled_time_delay_embedding_distance, euclidean_distance):
+//   out[k-1] = { mean over the simulated k-windows of (distance to the nearest human k-window) / k,   'Mean'
+//                the maximum of the same                                                             'Hausdorff'
+//                sum_{t<k} |s_t - h_t|  (euclidean_distance of the first k points) }
+// One block; D [Ls, Lh] point distances and the running window sums W_k = W_{k-1} + D shifted (the reference's
+// order of additions up to numpy's pairwise summation for k >= 8) live in the caller's work buffer.
+// ---------------------------------------------------------------------------
+namespace spb {
+__global__ void __launch_bounds__(256)
+tde_distances_kernel(const double *__restrict__ h_xy, int Lh, const double *__restrict__ s_xy, int Ls, double *work,
+                     double *__restrict__ out) {
+    double *D = work, *W = work + (int64_t)Ls * Lh, *best = W + (int64_t)Ls * Lh;
+    const int kmax = Lh < Ls ? Lh : Ls;
+    for (int idx = threadIdx.x; idx < Ls * Lh; idx += blockDim.x) {
+        const int i = idx / Lh, j = idx - i * Lh;
+        const double dx = s_xy[2 * i] - h_xy[2 * j], dy = s_xy[2 * i + 1] - h_xy[2 * j + 1];
+        D[idx] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        W[idx] = 0.0;
+    }
+    __syncthreads();
+    for (int k = 1; k <= kmax; ++k) {
+        const int nw = Ls - k + 1, nh = Lh - k + 1;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+            double b = INFINITY;
+            for (int j = 0; j < nh; ++j) {
+                const double w = W[(int64_t)i * Lh + j] + D[(int64_t)(i + k - 1) * Lh + (j + k - 1)];
+                W[(int64_t)i * Lh + j] = w;
+                b = fmin(b, fabs(w));
+            }
+            best[i] = b / (double)k;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0, mx = -INFINITY;
+            for (int i = 0; i < nw; ++i) { sum += best[i]; mx = fmax(mx, best[i]); }   // Python's sum(): in order
+            out[3 * (k - 1)] = sum / (double)nw;
+            out[3 * (k - 1) + 1] = mx;
+            out[3 * (k - 1) + 2] = W[0];
+        }
+        __syncthreads();
+    }
+}
+}  // namespace spb
+
+extern "C" int64_t spb_tde_work_bytes(int32_t Lh, int32_t Ls) {
+    if (Lh <= 0 || Ls <= 0) return 8;
+    return ((int64_t)2 * Lh * Ls + Ls) * 8;
+}
+
+extern "C" int spb_tde_distances(const double *d_h_xy, int32_t Lh, const double *d_s_xy, int32_t Ls, double *d_work,
+                                 int64_t work_bytes, double *d_out, spb_stream stream) {
+    SPB_CHECK_ARG(Lh >= 0 && Ls >= 0, "bad sizes");
+    if (Lh == 0 || Ls == 0) return SPB_OK;
+    SPB_CHECK_ARG(d_h_xy && d_s_xy && d_work && d_out, "null device pointer");
+    if (work_bytes < spb_tde_work_bytes(Lh, Ls)) {
+        spb::set_error("spb_tde_distances: work buffer too small (%lld < %lld bytes)", (long long)work_bytes,
+                       (long long)spb_tde_work_bytes(Lh, Ls));
+        return SPB_ERR_WORKSPACE;
+    }
+    spb::tde_distances_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_h_xy, Lh, d_s_xy, Ls, d_work, d_out);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+}
+
 static int reduce_blocks(int64_t n_groups) {
     int64_t blocks = (n_groups + 255) / 256;
     const int64_t cap = (int64_t)spb::num_sms() * 4;

@@ -187,6 +187,28 @@ def scanmatch_matrix(A, B, cfg: "ScoreConfig"):
     return F.cpu().numpy()
 
 
+def tde_table(human_xy, simulated_xy, device=None):
+    """[min(Lh, Ls), 3] f64 numpy table of spb_tde_distances for one pair: per window length k the 'Mean' and the
+    'Hausdorff' time-delay-embedding distance (visual_attention_metrics.py:332-390) and the sum of the first k
+    point distances.  Coordinates are taken as given (no rescaling)."""
+    _lib.require_cuda()
+    dev = torch.device(device or "cuda")
+    h = torch.as_tensor(np.ascontiguousarray(np.asarray(human_xy, dtype=np.float64)[:, :2])).to(dev)
+    s = torch.as_tensor(np.ascontiguousarray(np.asarray(simulated_xy, dtype=np.float64)[:, :2])).to(dev)
+    Lh, Ls = h.shape[0], s.shape[0]
+    kmax = min(Lh, Ls)
+    if kmax == 0:
+        return np.zeros((0, 3))
+    lib = _lib.load()
+    nbytes = lib.spb_tde_work_bytes(Lh, Ls)
+    work = torch.empty((nbytes // 8,), dtype=torch.float64, device=dev)
+    out = torch.empty((kmax, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spb_tde_distances(_lib.ptr(h), Lh, _lib.ptr(s), Ls, _lib.ptr(work), nbytes, _lib.ptr(out),
+                                         _lib.current_stream()), "spb_tde_distances")
+    return out.cpu().numpy()
+
+
 class Workspace:
     """Boundary-column workspace for with-duration strings longer than 256 symbols."""
 

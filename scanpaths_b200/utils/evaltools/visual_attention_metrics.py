@@ -1,6 +1,8 @@
 """Drop-in for the scanpath metrics of the reference's
-``utils/evaltools/visual_attention_metrics.py`` (SED :301-317, STDE :393-441) on
-the GPU (csrc/prep.cu + csrc/score_pairs.cu).  The saliency-map metrics of that
+``utils/evaltools/visual_attention_metrics.py`` (SED :301-317, STDE :393-441 and
+the STDE family's other entry points: euclidean_distance :205-218,
+time_delay_embedding_distance :332-390, scaled_time_delay_embedding_distance
+:444-492) on the GPU (csrc/prep.cu + csrc/score_pairs.cu).  The saliency-map metrics of that
 file (AUC_Judd, KLdiv, NSS) are never called by the reference's pipelines and are
 out of scope.  One pair per call; the batched path is ``scanpaths_b200.scoring``.
 """
@@ -47,3 +49,44 @@ def scaled_time_delay_embedding_similarity(human_scanpath, simulated_scanpath, i
     """visual_attention_metrics.py:393-441; None when either scanpath is empty."""
     v = float(_score(human_scanpath, simulated_scanpath, np.shape(image))[3])
     return None if np.isnan(v) else v
+
+
+def _xy(scanpath):
+    a = np.asarray(scanpath, dtype=np.float64)
+    return a.reshape(-1, a.shape[-1])[:, :2] if a.size else np.zeros((0, 2))
+
+
+def euclidean_distance(human_scanpath, simulated_scanpath, msg=False):
+    """visual_attention_metrics.py:205-218: the sum of the point distances of two equally long scanpaths, else
+    False."""
+    if len(human_scanpath) != len(simulated_scanpath):
+        if msg:
+            print('Error: The two sequences must have the same length!')
+        return False
+    if len(human_scanpath) == 0:
+        return 0.0
+    return float(S.tde_table(_xy(human_scanpath), _xy(simulated_scanpath))[-1, 2])
+
+
+def time_delay_embedding_distance(human_scanpath, simulated_scanpath, k=3, distance_mode='Mean', msg=False):
+    """visual_attention_metrics.py:332-390; False when k exceeds a scanpath's length or the mode is unknown."""
+    if len(human_scanpath) < k or len(simulated_scanpath) < k:
+        if msg:
+            print('ERROR: Too large value for the time-embedding vector dimension')
+        return False
+    if distance_mode not in ('Mean', 'Hausdorff'):
+        if msg:
+            print('ERROR: distance mode not defined.')
+        return False
+    row = S.tde_table(_xy(human_scanpath), _xy(simulated_scanpath))[k - 1]
+    return float(row[0] if distance_mode == 'Mean' else row[1])
+
+
+def scaled_time_delay_embedding_distance(human_scanpath, simulated_scanpath, image, toPlot=False, msg=False):
+    """visual_attention_metrics.py:444-492: coordinates rescaled by the image's largest dimension, then the mean
+    over k of the 'Mean' distances; None when either scanpath is empty."""
+    max_dim = float(max(np.shape(image)))
+    t = S.tde_table(_xy(human_scanpath) / max_dim, _xy(simulated_scanpath) / max_dim)
+    if len(t) == 0:
+        return None
+    return float(sum(t[:, 0]) / len(t))

@@ -352,8 +352,35 @@ def gen_align():
     print("alignment goldens:", len(cases), "cases; F shapes", [out["c%d_F" % k].shape for k in range(len(cases))][:6])
 
 
+def gen_tde():
+    """The helpers of the STDE family that the drivers reach only through scaled_time_delay_embedding_similarity
+    (visual_attention_metrics.py:205-218, 332-390, 444-492): euclidean_distance, time_delay_embedding_distance for
+    every k in both distance modes, scaled_time_delay_embedding_distance."""
+    ns = refload.load_reference("OSIE")
+    V = ns.vame
+    rng = np.random.default_rng(11)
+    pairs = [(human_paths(rng, 1, lh, lh)[0], pred_paths(rng, 1, ls, ls)[0])
+             for lh, ls in ((9, 12), (14, 16), (6, 3), (1, 5), (12, 12), (20, 9), (3, 3))]
+    out = {"n_cases": np.int64(len(pairs))}
+    stim = np.zeros((240, 320, 3), dtype=np.float32)
+    for c, (h, s) in enumerate(pairs):
+        kmax = min(len(h), len(s))
+        out["c%d_h" % c], out["c%d_s" % c] = h, s
+        out["c%d_mean" % c] = np.array([V.time_delay_embedding_distance(h, s, k=k, distance_mode="Mean") for k in range(1, kmax + 1)])
+        out["c%d_haus" % c] = np.array([V.time_delay_embedding_distance(h, s, k=k, distance_mode="Hausdorff") for k in range(1, kmax + 1)])
+        out["c%d_scaled" % c] = np.float64(V.scaled_time_delay_embedding_distance(h, s, stim))
+        e = V.euclidean_distance(h, s)
+        out["c%d_euclid" % c] = np.float64(np.nan if e is False else e)
+        assert V.time_delay_embedding_distance(h, s, k=kmax + 1) is False
+        assert V.time_delay_embedding_distance(h, s, k=1, distance_mode="nope") is False
+    np.savez_compressed(os.path.join(HERE, "vame_tde.npz"), **out)
+    print("TDE goldens:", len(pairs), "pairs; euclid defined for", int(sum(np.isfinite(out["c%d_euclid" % c]) for c in range(len(pairs)))))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("tde", "all"):
+        gen_tde()
     if what in ("align", "all"):
         gen_align()
     if what in ("scoring", "all"):

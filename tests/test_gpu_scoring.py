@@ -240,6 +240,31 @@ def test_mirror_match_returns_alignment_and_matrix(S, golden_dir):
     assert score == 0.0 and F.shape == (3, 1) and np.array_equal(align, [[-1, 3], [-1, 4]])
 
 
+def test_mirror_tde_family(S, golden_dir):
+    """euclidean_distance, time_delay_embedding_distance (every k, 'Mean' and 'Hausdorff'),
+    scaled_time_delay_embedding_distance (visual_attention_metrics.py:205-218, 332-390, 444-492) through
+    spb_tde_distances against the recorded reference outputs; the reference's False / None returns."""
+    from scanpaths_b200.utils.evaltools import visual_attention_metrics as V
+    g = np.load(os.path.join(golden_dir, "vame_tde.npz"))
+    stim = np.zeros((240, 320, 3), dtype=np.float32)
+    for c in range(int(g["n_cases"])):
+        h, s = g["c%d_h" % c], g["c%d_s" % c]
+        kmax = min(len(h), len(s))
+        for k in range(1, kmax + 1):
+            assert V.time_delay_embedding_distance(h, s, k=k) == pytest.approx(g["c%d_mean" % c][k - 1], rel=STDE_RTOL)
+            assert V.time_delay_embedding_distance(h, s, k=k, distance_mode="Hausdorff") == pytest.approx(
+                g["c%d_haus" % c][k - 1], rel=STDE_RTOL)
+        assert V.time_delay_embedding_distance(h, s, k=kmax + 1) is False
+        assert V.time_delay_embedding_distance(h, s, k=1, distance_mode="nope") is False
+        assert V.scaled_time_delay_embedding_distance(h, s, stim) == pytest.approx(float(g["c%d_scaled" % c]), rel=STDE_RTOL)
+        e = V.euclidean_distance(h, s)
+        if np.isnan(g["c%d_euclid" % c]):
+            assert e is False
+        else:
+            assert e == pytest.approx(float(g["c%d_euclid" % c]), rel=STDE_RTOL)
+    assert V.scaled_time_delay_embedding_distance(np.zeros((0, 3)), g["c0_s"], stim) is None
+
+
 def test_mirror_evaluation_drivers(S, golden_dir):
     from test_oracle_golden import _flat, _struct_lists
     from scanpaths_b200.utils import evaluation as E

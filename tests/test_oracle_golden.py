@@ -100,6 +100,27 @@ def test_match_alignment_and_matrix(golden_dir):
         assert np.array_equal(F, g["c%d_F" % k]), k
 
 
+def test_tde_family(golden_dir):
+    """euclidean_distance, time_delay_embedding_distance (every k, both modes), scaled_time_delay_embedding_distance
+    (visual_attention_metrics.py:205-218, 332-390, 444-492) against the recorded reference outputs."""
+    g = np.load(os.path.join(golden_dir, "vame_tde.npz"))
+    stim = np.zeros((240, 320, 3), dtype=np.float32)
+    for c in range(int(g["n_cases"])):
+        h, s = g["c%d_h" % c], g["c%d_s" % c]
+        kmax = min(len(h), len(s))
+        for k in range(1, kmax + 1):
+            assert O.time_delay_embedding_distance(h, s, k, "Mean") == pytest.approx(g["c%d_mean" % c][k - 1], rel=1e-13)
+            assert O.time_delay_embedding_distance(h, s, k, "Hausdorff") == pytest.approx(g["c%d_haus" % c][k - 1], rel=1e-13)
+        assert O.time_delay_embedding_distance(h, s, kmax + 1) is False
+        assert O.time_delay_embedding_distance(h, s, 1, "nope") is False
+        assert O.scaled_time_delay_embedding_distance(h, s, stim) == pytest.approx(float(g["c%d_scaled" % c]), rel=1e-13)
+        e = O.euclidean_distance(h, s)
+        if np.isnan(g["c%d_euclid" % c]):
+            assert e is False
+        else:
+            assert e == pytest.approx(float(g["c%d_euclid" % c]), rel=1e-13)
+
+
 def test_eval_drivers(golden_dir):
     g = _load(golden_dir, "eval_drivers.npz")
     humans, preds, N, K, S = _struct_lists(g)
