@@ -31,6 +31,16 @@ __device__ __forceinline__ void split_one(float v, __half &hi, __half &lo) {
     lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
 }
 
+// two values at once: one packed conversion each way instead of two scalar ones (same roundings, same results);
+// returns the (hi, lo) half2 pairs as the 32-bit words the operand tensors store
+__device__ __forceinline__ void split_two(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((v0 - hf.x) * kLoScale, (v1 - hf.y) * kLoScale);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
 // the exact fp32 value of an fp16 (hi, lo) pair, 8 consecutive channels
 __device__ __forceinline__ void load_h8(const __half *hi, const __half *lo, int64_t off, float (&v)[8]) {
     const uint4 a = *reinterpret_cast<const uint4 *>(hi + off), b = *reinterpret_cast<const uint4 *>(lo + off);
@@ -489,12 +499,11 @@ wino_input_kernel(const __half *__restrict__ h_hi, const __half *__restrict__ h_
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                __half hh[2], hl[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
+                uint32_t wh, wl;
+                split_two(t[j][0], t[j][1], wh, wl);
                 const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
-                *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
-                *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
+                *reinterpret_cast<uint32_t *>(u_hi + off) = wh;
+                *reinterpret_cast<uint32_t *>(u_lo + off) = wl;
             }
         }
     }
@@ -736,12 +745,11 @@ wino_input22_kernel(const __half *__restrict__ x_hi, const __half *__restrict__ 
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                __half hh[2], hl[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) split_one(t[j][e], hh[e], hl[e]);
+                uint32_t wh, wl;
+                split_two(t[j][0], t[j][1], wh, wl);
                 const int64_t off = ((int64_t)(j * 4 + i) * rows_pad + nt) * kE + c0;
-                *reinterpret_cast<uint32_t *>(u_hi + off) = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
-                *reinterpret_cast<uint32_t *>(u_lo + off) = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[1]) << 16);
+                *reinterpret_cast<uint32_t *>(u_hi + off) = wh;
+                *reinterpret_cast<uint32_t *>(u_lo + off) = wl;
             }
         }
     }
