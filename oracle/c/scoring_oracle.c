@@ -71,10 +71,11 @@ double spo_nw_score(const spo_cfg *c, const double *sub, const int32_t *A, long 
     double *prev = (double *)malloc(sizeof(double) * (m + 1)), *cur = (double *)malloc(sizeof(double) * (m + 1));
     for (int i = 0; i < nb * nb; ++i)
         if (sub[i] > maxsub) maxsub = sub[i];
-    for (long j = 0; j <= m; ++j) prev[j] = gap * (j + 1);
-    best = prev[0];
-    for (long j = 0; j <= m; ++j)
+    best = gap;                                  /* F[0][0] = gap * (0 + 1) */
+    for (long j = 0; j <= m; ++j) {
+        prev[j] = gap * (j + 1);
         if (prev[j] > best) best = prev[j];
+    }
     for (long i = 1; i <= n; ++i) {
         cur[0] = gap * (i + 1);
         if (cur[0] > best) best = cur[0];
